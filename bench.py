@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- the headline metric of BASELINE.json on this repo's engine.
+
+    metric : RAG queries/sec, 10M x 1536 bf16 corpus, top-10 (cosine), recall@10 vs numpy
+    step   : one batch of `--batch` queries searched against the whole corpus (VECTOR_SEARCH_AGG,
+             reference call site terraform/lab2-vector-search/main.tf:292)
+    value  : whole-job queries/sec with the queries already resident in HBM (CUDA events, max over ranks)
+    e2e    : same metric through the host-buffer C-ABI call sa_search_host (H2D of the fp32 queries and
+             D2H of the results inside the timed region)
+
+N > 1 (torchrun, one rank per GPU): the corpus is row-sharded, every rank searches its shard, one NCCL
+all-gather of the per-shard (cosine, global row) lists, merge kernel on every rank ("strong" scaling: the
+corpus and the batch are fixed as N grows).
+
+`--impl reference` times the CPU arm instead: the numpy brute-force oracle with all host
+threads on a bounded sample of the same workload.  It never touches the GPU engine.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "rag_queries_per_sec_10Mx1536_top10"
+UNIT = "queries/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=10_000_000)
+    ap.add_argument("--dim", type=int, default=1536)
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--cta-group", type=int, default=0, help="0 auto, 1, 2")
+    ap.add_argument("--recall-queries", type=int, default=8, help="queries checked against numpy over ALL rows")
+    ap.add_argument("--cpu-sample-queries", type=int, default=256)
+    ap.add_argument("--cpu-sample-rows", type=int, default=524_288)
+    ap.add_argument("--no-cpu", action="store_true", help="skip cpu_baseline / recall (profiling runs)")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return f"{a.rows}x{a.dim} bf16 corpus, batch {a.batch}, top-{a.k}, cosine"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "tflops_burst": d["bf16_tflops"],
+                "tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU arm (oracle; the only place besides tests/ and smoke() that touches oracle/)
+# ----------------------------------------------------------------------------------------------------
+def cpu_sample_run(q_bits, chunks, k, full_rows):
+    """Time numpy brute force on (queries x sample rows); return (qps scaled to `full_rows`, seconds)."""
+    from oracle import bruteforce as bf
+    t0 = time.perf_counter()
+    bf.cosine_topk_sgemm(q_bits, chunks, k)
+    dt = time.perf_counter() - t0
+    rows = sum(len(c) for _, c in chunks)
+    qps_full = (len(q_bits) * rows / dt) / full_rows
+    return qps_full, dt
+
+
+def run_reference(a):
+    """--impl reference: the reference's own (CPU) way of answering the query, per BASELINE.md section 4."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import bruteforce as bf
+    nq, rows = a.cpu_sample_queries, a.cpu_sample_rows
+    chunks = []
+    for c in range((rows + bf.CHUNK_ROWS - 1) // bf.CHUNK_ROWS):
+        m = min(bf.CHUNK_ROWS, rows - c * bf.CHUNK_ROWS)
+        chunks.append((c * bf.CHUNK_ROWS, bf.synth_rows(1234, c, m, a.dim)))
+    q = bf.synth_queries(4321, nq, a.dim, chunks[0][1])
+    vals = []
+    for _ in range(a.warmup):
+        cpu_sample_run(q[: max(8, nq // 8)], chunks[:1], a.k, a.rows)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        vals.append(cpu_sample_run(q, chunks, a.k, a.rows)[0])
+    dt = time.perf_counter() - t0
+    v = float(np.median(vals))
+    cores = os.cpu_count()
+    sample = f"{nq} queries x {rows} rows per step (of {a.batch} x {a.rows}); QPS scaled by rows"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic (numpy PCG64, oracle.synth_rows seed 1234/4321)",
+        "config": {"workload": workload_name(a), "k": a.k, "cpu": "numpy fp32 sgemm brute force, all host threads"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.idx = device_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        sm, mx, reasons, pw = [], [], set(), []
+        for t, line in self.rows:
+            if t < t0 or t > t1:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------
+def fill_corpus(ix, n_local, dim, seed):
+    """Synthetic corpus generated on the device (Philox) straight into the bf16 rows, then committed."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    step = 1 << 18
+    for lo in range(0, n_local, step):
+        m = min(step, n_local - lo)
+        x = torch.randn((m, dim), generator=g, device="cuda", dtype=torch.float32)
+        x *= torch.exp(torch.empty((m, 1), device="cuda").uniform_(-0.7, 0.7, generator=g))
+        ix.rows[lo:lo + m].copy_(x)
+    ix.commit(0, n_local)
+
+
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    from qsa_b200.engine import VectorIndex
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        if world == 1 and a.gpus > 1:
+            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    n_total, dim, B, k = a.rows, a.dim, a.batch, a.k
+    lo_row = rank * n_total // world
+    hi_row = (rank + 1) * n_total // world
+    n_local = hi_row - lo_row
+
+    ix = VectorIndex(dim=dim, capacity=n_local, max_batch=B, max_k=k, device=local)
+    if a.cta_group:
+        ix.set_option("cta_group", a.cta_group)
+    fill_corpus(ix, n_local, dim, seed=1234 + rank)
+    g = torch.Generator(device="cuda").manual_seed(4321)
+    q_f32 = torch.randn((B, dim), generator=g, device="cuda", dtype=torch.float32)
+    # plant half of the queries next to rows of rank 0's shard start (known neighbours exist)
+    q_bf16 = q_f32.to(torch.bfloat16)
+    q_host = q_bf16.to(torch.float32).cpu().numpy()  # host fp32 queries (exactly representable in bf16)
+    torch.cuda.synchronize()
+
+    gathered_s = torch.empty((world, B, k), dtype=torch.float64, device="cuda") if world > 1 else None
+    gathered_i = torch.empty((world, B, k), dtype=torch.int64, device="cuda") if world > 1 else None
+
+    def step_device():
+        if world == 1:
+            return ix.search(q_bf16, k)
+        s, i, s64 = ix.search(q_bf16, k, want_score64=True)
+        gi = torch.where(i >= 0, i.to(torch.int64) + lo_row, torch.full_like(i, -1, dtype=torch.int64))
+        dist.all_gather_into_tensor(gathered_s, s64)
+        dist.all_gather_into_tensor(gathered_i, gi)
+        return ix.merge_shards(gathered_s, gathered_i)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for _ in range(a.warmup):
+        out = step_device()
+    barrier()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+
+    # ---- timed: device-resident queries
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    scan_ms, scan_launches, kernels = [], 0, 0
+    barrier()
+    t_w0 = time.perf_counter()
+    ev0.record()
+    for _ in range(a.steps):
+        out = step_device()
+    ev1.record()
+    barrier()
+    t_w1 = time.perf_counter()
+    ms_total = ev0.elapsed_time(ev1)
+    t = ix.last_timing()
+    # per-launch scan time of the LAST step (events live inside the C-ABI, on the launching stream)
+    scan_ms_last = t.scan_ms
+    launches_per_step = t.launches
+    kernels_per_step = t.kernels + (0 if world == 1 else 1)
+
+    # a second short loop that reads the scan events every step (still back to back on the device)
+    scan_times = []
+    barrier()
+    for _ in range(min(a.steps, 5)):
+        step_device()
+        scan_times.append(ix.last_timing().scan_ms)
+    barrier()
+    scan_ms_avg = float(np.mean(scan_times)) if scan_times else scan_ms_last
+
+    # ---- timed: e2e with HOST buffers through sa_search_host (+ all-gather/merge for N>1)
+    def step_host():
+        if world == 1:
+            return ix.search_host(q_host, k)
+        # N>1: host queries -> every rank's shard; results gathered on device, final D2H
+        qd = torch.from_numpy(q_host).cuda(non_blocking=False)
+        s, i, s64 = ix.search(qd, k, want_score64=True)
+        gi = torch.where(i >= 0, i.to(torch.int64) + lo_row, torch.full_like(i, -1, dtype=torch.int64))
+        dist.all_gather_into_tensor(gathered_s, s64)
+        dist.all_gather_into_tensor(gathered_i, gi)
+        fs, fi = ix.merge_shards(gathered_s, gathered_i)
+        return fs.cpu().numpy(), fi.cpu().numpy()
+
+    for _ in range(2):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        res_host = step_host()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    time.sleep(0.2)
+    sampler.stop()
+    clocks = sampler.summary(t_w0, t_w1)
+
+    # max over ranks
+    if world > 1:
+        tt = torch.tensor([ms_total, e2e_s, scan_ms_avg], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total, e2e_s, scan_ms_avg = [float(x) for x in tt.tolist()]
+
+    qps = B * a.steps / (ms_total * 1e-3)
+    e2e_qps = B * a.steps / e2e_s
+
+    result = None
+    if rank == 0:
+        peaks = measured_peaks()
+        flops_launch = 2.0 * B * n_local * dim / launches_per_step
+        bytes_launch = n_local * dim * 2.0 + n_local * 4.0 + (B * dim * 2.0 + B * k * 8.0) / launches_per_step
+        t_launch = scan_ms_avg / launches_per_step * 1e-3
+        ach_tf = flops_launch / t_launch / 1e12
+        ach_gbs = bytes_launch / t_launch / 1e9
+        ridge = peaks["tflops_sustained"] * 1e3 / peaks["hbm_gbs"]
+        tensor_bound = (B / launches_per_step) >= ridge  # arithmetic intensity of a launch = its batch, flop/byte
+        if tensor_bound:
+            roof = {"bound": "tensor", "achieved": ach_tf, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": ach_tf / peaks["tflops_sustained"],
+                    "peak_kind": f"{peaks['source']} cuBLAS bf16 sustained (kernel timed inside a long step)"}
+        else:
+            roof = {"bound": "hbm", "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach_gbs / peaks["hbm_gbs"], "peak_kind": f"{peaks['source']} copy bandwidth"}
+        roof.update({"traffic": None, "kernel": "sa_scan_kernel", "launch_ms": t_launch * 1e3,
+                     "launches_per_step": launches_per_step, "achieved_gbs": ach_gbs, "achieved_tflops": ach_tf,
+                     "hbm_frac": ach_gbs / peaks["hbm_gbs"], "tensor_frac_sustained": ach_tf / peaks["tflops_sustained"],
+                     "tensor_frac_burst": ach_tf / peaks["tflops_burst"], "scan_share_of_step": scan_ms_avg / (ms_total / a.steps)})
+        result = {
+            "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic (device Philox normals, per-row log-uniform scale; not pre-normalised)",
+            "config": {"workload": workload_name(a), "rows_per_gpu": n_local, "batch": B, "k": k, "dim": dim,
+                       "parallelism": f"row-shard x{world}" if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2 (corpus shard %.1f GB per step)" % (n_local * dim * 2 / 1e9),
+                       "cta_group": a.cta_group or "auto"},
+            "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": B * dim * 4, "d2h_bytes_per_step": B * k * (8 if world == 1 else 12)},
+            "gpu_launches": int(kernels_per_step * a.steps),
+            "clocks": clocks, "roofline": roof,
+        }
+
+    # ---- outside the timed region: recall vs numpy + CPU baseline (rank 0, N=1)
+    if rank == 0 and world == 1 and not a.no_cpu:
+        from oracle import bruteforce as bf
+        got_s, got_i = [x.cpu().numpy() for x in out]
+        nrq = min(a.recall_queries, B)
+        qb = q_bf16[:nrq].view(torch.int16).cpu().numpy().view(np.uint16)
+
+        def dev_chunks(limit=None):
+            step = 1 << 18
+            n = n_local if limit is None else min(limit, n_local)
+            for lo in range(0, n, step):
+                m = min(step, n - lo)
+                yield lo, ix.rows[lo:lo + m].view(torch.int16).cpu().numpy().view(np.uint16)
+
+        rs, ri = bf.cosine_topk_fast(qb, dev_chunks(), k)
+        rep = bf.compare_topk(got_i[:nrq], got_s[:nrq], ri, rs)
+        rep_host = bf.compare_topk(res_host[1][:nrq], res_host[0][:nrq], ri, rs)
+        result["recall"] = {"queries_checked": nrq, "rows": n_local, "recall_at_k": rep["recall"],
+                            "strict_order": rep["strict_order"], "max_abs_dscore": rep["max_abs_dscore"],
+                            "e2e_strict_order": rep_host["strict_order"]}
+        # CPU baseline on a bounded sample of the same device data
+        nsq = min(a.cpu_sample_queries, B)
+        qs = q_bf16[:nsq].view(torch.int16).cpu().numpy().view(np.uint16)
+        chunks = list(dev_chunks(a.cpu_sample_rows))
+        cpu_sample_run(qs[:16], chunks[:1], k, n_total)  # warm BLAS threads
+        v, dt = cpu_sample_run(qs, chunks, k, n_total)
+        result["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                  "sample": f"{nsq} queries x {sum(len(c) for _, c in chunks)} rows in {dt:.1f}s "
+                                            f"(numpy fp32 sgemm brute force, QPS scaled to {n_total} rows)"}
+    elif rank == 0:
+        result.setdefault("cpu_baseline", None)
+
+    if rank == 0:
+        print(json.dumps(result))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

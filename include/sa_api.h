@@ -1,0 +1,116 @@
+/* sa_api.h -- C ABI of the B200-native vector-search engine (libsa_b200.so).
+ *
+ * This is the drop-in boundary for the one data-parallel path of confluentinc/quickstart-streaming-agents:
+ * the Lab2 RAG lookup that the reference runs as Flink SQL inside Confluent Cloud against a MongoDB Atlas
+ * vector index.  The reference has no FFI of its own (it is Python glue + Terraform),
+ * so each entry point cites the reference statement / script whose work it takes over.  A Python caller
+ * binds these with ctypes (quickstart-streaming-agents_b200/capi.py; INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative sa_status otherwise; sa_last_error() has the detail;
+ *   - "dev" pointers are CUDA device pointers on the engine's device, "host" pointers are ordinary memory;
+ *   - the caller owns every data buffer (a torch tensor is just an allocator here); the library owns only
+ *     its own scratch, pinned staging and TMA descriptors and never copies the corpus;
+ *   - `stream` is a cudaStream_t passed as an integer (0 = the legacy default stream); device entry points
+ *     are asynchronous on it, *_host entry points block until their result is in host memory;
+ *   - an engine serves one CUDA device and is not re-entrant;
+ *   - there is no CPU fallback: on a device that is not sm_100 sa_engine_create fails with SA_ERR_DEVICE.
+ */
+#ifndef SA_API_H_
+#define SA_API_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sa_engine sa_engine;
+
+typedef enum sa_status {
+  SA_OK = 0,
+  SA_ERR_CUDA = -1,     /* a CUDA runtime / driver call failed */
+  SA_ERR_ARG = -2,      /* bad argument (null, range, alignment, dim % 64 != 0, k > max_k ...) */
+  SA_ERR_COMM = -3,     /* reserved for collective errors (the all-gather itself runs in torch.distributed) */
+  SA_ERR_CAPACITY = -4, /* append past capacity_rows, batch past max_batch */
+  SA_ERR_DEVICE = -5    /* device is not compute capability 10.x */
+} sa_status;
+
+#define SA_MAX_K 28 /* candidate lists hold k + 4 entries, at most 32 */
+
+int sa_version(void);
+const char* sa_strerror(int rc);
+const char* sa_last_error(void); /* thread-local detail of the last failure on this thread */
+
+/* --- engine -------------------------------------------------------------------------------------------
+ * Replaces the external vector table + index declaration:
+ *   CREATE TABLE documents_vectordb_lab2 (... embedding ARRAY<FLOAT>) WITH ('connector'='mongodb',
+ *   'mongodb.index'='vector_index', 'mongodb.embedding_column'='embedding', ...)
+ *   (terraform/lab2-vector-search/main.tf:215) and the index definition {numDimensions 1536, similarity cosine}
+ *   (assets/pre-setup/MongoDB-Setup.md:72-83, scripts/common/validate.py:56-61,167-180).
+ * dim must be a multiple of 64 (1536 and 768 are); capacity_rows < 2^31; max_k <= SA_MAX_K. */
+int sa_engine_create(sa_engine** out, int device, int dim, int64_t capacity_rows, int max_batch, int max_k);
+void sa_engine_destroy(sa_engine* e);
+
+/* Attach caller-owned device storage: rows_bf16 is [capacity_rows x dim] row-major bf16 (16-byte aligned),
+ * inv_norm is [capacity_rows] fp32.  n_valid rows are taken as already committed (their inv_norm valid). */
+int sa_corpus_bind(sa_engine* e, void* rows_bf16_dev, float* inv_norm_dev, int64_t n_valid);
+
+/* --- ingest (the "documents -> documents_embed -> MongoDB sink" half of Lab2, LAB2-Walkthrough.md:41-51,
+ *     fed by scripts/publish_docs.py:225-351; embeddings arrive as ARRAY<FLOAT>, main.tf:141,215) ------- */
+/* Rows [first_row, first_row+n_new) were written in place as bf16 by the caller: compute their inverse
+ * L2 norms and publish them (first_row must equal the current row count). */
+int sa_corpus_commit(sa_engine* e, int64_t first_row, int64_t n_new, uintptr_t stream);
+/* Convert n_new fp32 rows (device) to bf16 (round-to-nearest-even), append, norm, publish. */
+int sa_corpus_append_f32(sa_engine* e, const float* rows_f32_dev, int64_t n_new, uintptr_t stream);
+/* Same from host memory (staged through pinned memory in chunks); blocking. */
+int sa_corpus_append_host_f32(sa_engine* e, const float* rows_f32_host, int64_t n_new);
+/* Forget all rows -- what scripts/common/clear_mongodb.py:98-158 (delete_many({})) does to the collection. */
+int sa_corpus_reset(sa_engine* e);
+int64_t sa_corpus_rows(const sa_engine* e);
+
+/* --- search: LATERAL TABLE(VECTOR_SEARCH_AGG(documents_vectordb_lab2, DESCRIPTOR(embedding),
+ *     qe.embedding, k))  (terraform/lab2-vector-search/main.tf:292; LAB3-Walkthrough.md:343-350;
+ *     LAB4-Walkthrough.md:302-309) for a batch of nq query vectors --------------------------------------
+ * Result for query i: out_idx[i*k .. i*k+k) = shard-local rows of the k most cosine-similar committed corpus
+ * rows, descending by cosine, ties by ascending row; out_score = those cosines (fp32 rounding of the fp64
+ * value); slots past the number of eligible rows hold idx -1 / score -inf.  All-zero corpus rows are never
+ * returned.  out_score64 (optional, may be NULL) receives the unrounded cosines for a cross-shard merge. */
+int sa_search(sa_engine* e, const void* q_bf16_dev, int nq, int k, float* out_score_dev, int32_t* out_idx_dev,
+              double* out_score64_dev, uintptr_t stream);
+/* Queries as fp32 (the ML_PREDICT output type, terraform/core/main.tf:500,534): rounded to bf16 first. */
+int sa_search_f32(sa_engine* e, const float* q_f32_dev, int nq, int k, float* out_score_dev, int32_t* out_idx_dev,
+                  double* out_score64_dev, uintptr_t stream);
+/* End-to-end call with HOST buffers: H2D of the queries, search, D2H of the results; blocking. */
+int sa_search_host(sa_engine* e, const float* q_f32_host, int nq, int k, float* out_score_host,
+                   int32_t* out_idx_host);
+
+/* --- multi-GPU: after each rank searched its row shard and the per-rank (score64, global row) lists were
+ *     all-gathered into [n_shards x nq x k] buffers, merge to the global top-k. --- */
+int sa_merge_shards(sa_engine* e, const double* score64_dev, const int64_t* global_idx_dev, int n_shards, int nq,
+                    int k, float* out_score_dev, int64_t* out_idx_dev, uintptr_t stream);
+
+/* --- observability ------------------------------------------------------------------------------------
+ * CUDA-event times of the most recent search on this engine (synchronises on its last event):
+ * scan_ms = sum over its scan-kernel launches, total_ms = first scan start to last merge end,
+ * bytes / flops = ALGORITHMIC work of that search, launches = scan launches,
+ * kernels = all kernels the search launched. */
+int sa_last_timing(sa_engine* e, float* scan_ms, float* total_ms, double* bytes, double* flops, int* launches,
+                   int* kernels);
+/* Options: "cta_group" = 0 (auto) | 1 | 2;  "max_launch_qblocks" = cap on query blocks per scan launch. */
+int sa_set_option(sa_engine* e, const char* name, int64_t value);
+int sa_get_info(const sa_engine* e, const char* name, int64_t* value); /* "num_sms", "dim", "capacity", "n_rows" */
+
+/* Test hook: raw fp32 Q.C^T accumulators of one 256-row corpus tile for the first nq queries,
+ * out_dots_dev is [ceil(nq/(128*cg))*128*cg x 256].  Runs the scan kernel's debug instantiation. */
+int sa_debug_tile_dots(sa_engine* e, const void* q_bf16_dev, int nq, int tile, int cta_group, float* out_dots_dev,
+                       uintptr_t stream);
+
+/* Pinned host memory for callers that want truly asynchronous staging. */
+int sa_host_alloc(void** out, uint64_t bytes);
+int sa_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SA_API_H_ */

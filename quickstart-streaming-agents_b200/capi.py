@@ -1,0 +1,91 @@
+"""ctypes binding of libsa_b200.so -- one Python function per entry point of include/sa_api.h.
+
+No compute happens in this file and there is no fallback: if the shared library is missing or a call
+fails, an exception is raised (``SaLibraryMissing`` / ``SaError``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsa_b200.so")
+
+SA_OK = 0
+SA_ERR_CUDA = -1
+SA_ERR_ARG = -2
+SA_ERR_COMM = -3
+SA_ERR_CAPACITY = -4
+SA_ERR_DEVICE = -5
+SA_MAX_K = 28
+
+# every symbol include/sa_api.h declares (tests check the .so exports each of them)
+EXPORTS = (
+    "sa_version", "sa_strerror", "sa_last_error", "sa_engine_create", "sa_engine_destroy", "sa_corpus_bind",
+    "sa_corpus_commit", "sa_corpus_append_f32", "sa_corpus_append_host_f32", "sa_corpus_reset", "sa_corpus_rows",
+    "sa_search", "sa_search_f32", "sa_search_host", "sa_merge_shards", "sa_last_timing", "sa_set_option",
+    "sa_get_info", "sa_debug_tile_dots", "sa_host_alloc", "sa_host_free",
+)
+
+
+class SaLibraryMissing(RuntimeError):
+    pass
+
+
+class SaError(RuntimeError):
+    def __init__(self, rc: int, what: str, detail: str):
+        super().__init__(f"{what}: {detail} (rc={rc})")
+        self.rc = rc
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libsa_b200.so (built in-tree by ``__graft_entry__.build()`` / ``make -C csrc``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SaLibraryMissing(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, u64, f32p = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.POINTER(C.c_float)
+    sig = {
+        "sa_version": (i32, []),
+        "sa_strerror": (C.c_char_p, [i32]),
+        "sa_last_error": (C.c_char_p, []),
+        "sa_engine_create": (i32, [C.POINTER(vp), i32, i32, i64, i32, i32]),
+        "sa_engine_destroy": (None, [vp]),
+        "sa_corpus_bind": (i32, [vp, vp, vp, i64]),
+        "sa_corpus_commit": (i32, [vp, i64, i64, vp]),
+        "sa_corpus_append_f32": (i32, [vp, vp, i64, vp]),
+        "sa_corpus_append_host_f32": (i32, [vp, vp, i64]),
+        "sa_corpus_reset": (i32, [vp]),
+        "sa_corpus_rows": (i64, [vp]),
+        "sa_search": (i32, [vp, vp, i32, i32, vp, vp, vp, vp]),
+        "sa_search_f32": (i32, [vp, vp, i32, i32, vp, vp, vp, vp]),
+        "sa_search_host": (i32, [vp, vp, i32, i32, vp, vp]),
+        "sa_merge_shards": (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp]),
+        "sa_last_timing": (i32, [vp, f32p, f32p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i32),
+                                 C.POINTER(i32)]),
+        "sa_set_option": (i32, [vp, C.c_char_p, i64]),
+        "sa_get_info": (i32, [vp, C.c_char_p, C.POINTER(i64)]),
+        "sa_debug_tile_dots": (i32, [vp, vp, i32, i32, i32, vp, vp]),
+        "sa_host_alloc": (i32, [C.POINTER(vp), u64]),
+        "sa_host_free": (i32, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != SA_OK:
+        lib = load()
+        detail = lib.sa_last_error().decode() or lib.sa_strerror(rc).decode()
+        raise SaError(rc, what, detail)

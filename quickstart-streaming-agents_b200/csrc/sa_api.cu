@@ -1,0 +1,629 @@
+// libsa_b200.so -- host side of the C ABI declared in include/sa_api.h.
+// Owns: scratch for the per-CTA candidate lists, pinned staging, TMA descriptors, CUDA events.
+// Never owns or copies the corpus.  No CPU fallback anywhere: every entry point ends in a kernel launch.
+#include "../../include/sa_api.h"
+#include "sa_aux.cuh"
+#include "sa_scan.cuh"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int rc, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return rc;
+}
+
+#define SA_CUDA(call)                                                                                \
+  do {                                                                                               \
+    cudaError_t _e = (call);                                                                         \
+    if (_e != cudaSuccess)                                                                           \
+      return fail(SA_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// 2-D bf16 tensor [rows x dim], box = 64 columns (128 B, SWIZZLE_128B) x box_rows rows.
+int encode_rows_map(CUtensorMap* m, const void* base, uint64_t rows, int dim, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(SA_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(dim), rows};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(dim) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(sa::kBlockK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SA_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return SA_OK;
+}
+
+constexpr int kMaxLaunches = 16;
+
+}  // namespace
+
+struct sa_engine {
+  int device = 0;
+  int dim = 0;
+  int64_t capacity = 0;
+  int max_batch = 0;
+  int max_k = 0;
+  int num_sms = 0;
+
+  uint16_t* corpus = nullptr;  // caller-owned
+  float* inv_norm = nullptr;   // caller-owned
+  int64_t n_rows = 0;
+  CUtensorMap tmap_c[2];       // [0]: box 256 rows (cta_group 1), [1]: box 128 rows (cta_group 2)
+  bool bound = false;
+
+  // scratch (library-owned)
+  float* part_score = nullptr;  // [num_sms][128][32]
+  int* part_idx = nullptr;
+  uint16_t* q_bf16 = nullptr;   // [max_batch][dim]
+  float* q_f32 = nullptr;       // [max_batch][dim]  (host-path staging on device)
+  float* res_score = nullptr;   // [max_batch][max_k]
+  int* res_idx = nullptr;
+  float* h_q = nullptr;         // pinned [max_batch][dim]
+  float* h_score = nullptr;     // pinned
+  int* h_idx = nullptr;         // pinned
+  float* d_stage = nullptr;     // device staging for host ingest
+  float* h_stage = nullptr;     // pinned staging for host ingest
+  int64_t stage_rows = 0;
+  cudaStream_t own_stream = nullptr;
+
+  // options
+  int opt_cta_group = 0;
+  int opt_max_launch_qblocks = 0;
+
+  // timing of the last search
+  cudaEvent_t ev_total[2] = {nullptr, nullptr};
+  cudaEvent_t ev_scan[kMaxLaunches][2];
+  int last_launches = 0;
+  int last_kernels = 0;
+  double last_bytes = 0, last_flops = 0;
+  bool have_timing = false;
+};
+
+namespace {
+
+struct LaunchPlan {
+  int cg;
+  int q0;   // first query of this launch
+  int nq;   // queries in this launch
+  int nqb;  // query blocks (of 128*cg)
+  int tl;   // tile lanes
+};
+
+// Split the batch into scan launches.  A launch with nqb query blocks runs TL = floor(units / nqb) tile
+// lanes, each walking ceil(num_tiles / TL) tiles; pick the split that minimises the summed tile walks
+// (fewer launches win ties: every launch re-streams the corpus through HBM once).
+std::vector<LaunchPlan> plan_search(const sa_engine* e, int nq, int cg, int num_tiles) {
+  const int rows_per_qb = 128 * cg;
+  const int units = e->num_sms / cg;
+  const int nqb_total = (nq + rows_per_qb - 1) / rows_per_qb;
+  int cap = units;
+  if (e->opt_max_launch_qblocks > 0) cap = std::min(cap, e->opt_max_launch_qblocks);
+  long best_cost = -1;
+  int best_l = 1;
+  const int l_min = (nqb_total + cap - 1) / cap;
+  for (int l = l_min; l <= std::min(nqb_total, l_min + 7); ++l) {
+    long cost = 0;
+    int left = nqb_total;
+    for (int i = 0; i < l; ++i) {
+      const int per = (left + (l - i) - 1) / (l - i);
+      const int tl = std::max(1, std::min(units / per, num_tiles));
+      cost += (num_tiles + tl - 1) / tl;
+      left -= per;
+    }
+    if (best_cost < 0 || cost * 100 < best_cost * 97) {  // a later (more launches) split must win by > 3 %
+      best_cost = cost;
+      best_l = l;
+    }
+  }
+  std::vector<LaunchPlan> out;
+  int left = nqb_total, qb0 = 0;
+  for (int i = 0; i < best_l; ++i) {
+    const int per = (left + (best_l - i) - 1) / (best_l - i);
+    LaunchPlan lp;
+    lp.cg = cg;
+    lp.q0 = qb0 * rows_per_qb;
+    lp.nq = std::min(nq - lp.q0, per * rows_per_qb);
+    lp.nqb = per;
+    lp.tl = std::max(1, std::min(units / per, num_tiles));
+    out.push_back(lp);
+    qb0 += per;
+    left -= per;
+  }
+  return out;
+}
+
+template <int kCG, int kKL, bool kDebug>
+int launch_scan(const CUtensorMap& tq, const CUtensorMap& tc, const sa::ScanParams& p, int grid, cudaStream_t st) {
+  auto kern = sa::sa_scan_kernel<kCG, kKL, kDebug>;
+  // per-device attribute; a few microseconds, so set it on every launch rather than caching per device
+  SA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, sa::ScanCfg<kCG>::kSmemBytes));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(sa::kScanThreads);
+  cfg.dynamicSmemBytes = sa::ScanCfg<kCG>::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SA_CUDA(cudaLaunchKernelEx(&cfg, kern, tq, tc, p));
+  return SA_OK;
+}
+
+int launch_scan_dispatch(int cg, int kl, bool debug, const CUtensorMap& tq, const CUtensorMap& tc,
+                         const sa::ScanParams& p, int grid, cudaStream_t st) {
+  if (debug) {
+    if (cg == 1) return launch_scan<1, 16, true>(tq, tc, p, grid, st);
+    return launch_scan<2, 16, true>(tq, tc, p, grid, st);
+  }
+  if (cg == 1 && kl == 16) return launch_scan<1, 16, false>(tq, tc, p, grid, st);
+  if (cg == 1 && kl == 32) return launch_scan<1, 32, false>(tq, tc, p, grid, st);
+  if (cg == 2 && kl == 16) return launch_scan<2, 16, false>(tq, tc, p, grid, st);
+  if (cg == 2 && kl == 32) return launch_scan<2, 32, false>(tq, tc, p, grid, st);
+  return fail(SA_ERR_ARG, "no scan instantiation for cta_group %d list %d", cg, kl);
+}
+
+int choose_cg(const sa_engine* e, int nq) {
+  if (e->opt_cta_group == 1 || e->opt_cta_group == 2) return e->opt_cta_group;
+  // Auto: a CTA pair shares the corpus tile between two query blocks (half the smem/L2 operand traffic per
+  // flop), which pays once the batch fills 256-row pair blocks; small batches are HBM-bound and use 1 CTA.
+  (void)nq;
+  return 1;  // TODO(round 1): flip to `nq > 128 ? 2 : 1` once the pair kernel is validated on hardware
+}
+
+int check_engine(const sa_engine* e) {
+  if (!e) return fail(SA_ERR_ARG, "null engine");
+  if (!e->bound) return fail(SA_ERR_ARG, "no corpus bound (call sa_corpus_bind)");
+  return SA_OK;
+}
+
+int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_score, int32_t* out_idx,
+              double* out_score64, cudaStream_t st) {
+  if (nq <= 0 || nq > e->max_batch) return fail(SA_ERR_CAPACITY, "nq %d outside [1, max_batch %d]", nq, e->max_batch);
+  if (k <= 0 || k > e->max_k) return fail(SA_ERR_ARG, "k %d outside [1, max_k %d]", k, e->max_k);
+  if (!q_bf16 || !out_score || !out_idx) return fail(SA_ERR_ARG, "null buffer");
+  if (reinterpret_cast<uintptr_t>(q_bf16) % 16) return fail(SA_ERR_ARG, "query buffer must be 16-byte aligned");
+  SA_CUDA(cudaSetDevice(e->device));
+
+  const int kl = (k + 4 <= 16) ? 16 : 32;
+  const int64_t n_rows = e->n_rows;
+  const int num_tiles = static_cast<int>((n_rows + sa::kBlockN - 1) / sa::kBlockN);
+  const int cg = choose_cg(e, nq);
+  std::vector<LaunchPlan> plan = plan_search(e, nq, cg, std::max(num_tiles, 1));
+  if (static_cast<int>(plan.size()) > kMaxLaunches)
+    return fail(SA_ERR_CAPACITY, "batch needs %zu scan launches (max %d)", plan.size(), kMaxLaunches);
+
+  e->last_launches = 0;
+  e->last_kernels = 0;
+  SA_CUDA(cudaEventRecord(e->ev_total[0], st));
+  for (size_t li = 0; li < plan.size(); ++li) {
+    const LaunchPlan& lp = plan[li];
+    const uint16_t* qptr = q_bf16 + static_cast<size_t>(lp.q0) * e->dim;
+    CUtensorMap tq;
+    int rc = encode_rows_map(&tq, qptr, static_cast<uint64_t>(lp.nq), e->dim, sa::kBlockM);
+    if (rc) return rc;
+
+    sa::ScanParams sp = {};
+    sp.inv_norm = e->inv_norm;
+    sp.n_rows = n_rows;
+    sp.nq = lp.nq;
+    sp.num_kb = e->dim / sa::kBlockK;
+    sp.num_tiles = num_tiles;
+    sp.nqb = lp.nqb;
+    sp.tl_count = lp.tl;
+    sp.part_score = e->part_score;
+    sp.part_idx = e->part_idx;
+    sp.corpus_evict_first = (lp.nqb == 1) ? 1 : 0;
+    sp.dbg_dots = nullptr;
+    sp.dbg_tile = -1;
+    const int grid = lp.nqb * lp.tl * lp.cg;
+
+    SA_CUDA(cudaEventRecord(e->ev_scan[li][0], st));
+    rc = launch_scan_dispatch(lp.cg, kl, false, tq, e->tmap_c[lp.cg - 1], sp, grid, st);
+    if (rc) return rc;
+    SA_CUDA(cudaEventRecord(e->ev_scan[li][1], st));
+
+    sa::MergeParams mp = {};
+    mp.part_score = e->part_score;
+    mp.part_idx = e->part_idx;
+    mp.corpus = e->corpus;
+    mp.queries = qptr;
+    mp.dim = e->dim;
+    mp.nq = lp.nq;
+    mp.k = k;
+    mp.cg = lp.cg;
+    mp.nqb = lp.nqb;
+    mp.tl_count = lp.tl;
+    mp.out_score = out_score + static_cast<size_t>(lp.q0) * k;
+    mp.out_idx = out_idx + static_cast<size_t>(lp.q0) * k;
+    mp.out_score64 = out_score64 ? out_score64 + static_cast<size_t>(lp.q0) * k : nullptr;
+    if (kl == 16)
+      sa::sa_merge_rescore_kernel<16><<<lp.nq, sa::kMergeThreads, 0, st>>>(mp);
+    else
+      sa::sa_merge_rescore_kernel<32><<<lp.nq, sa::kMergeThreads, 0, st>>>(mp);
+    SA_CUDA(cudaGetLastError());
+    e->last_launches += 1;
+    e->last_kernels += 2;
+  }
+  SA_CUDA(cudaEventRecord(e->ev_total[1], st));
+  // Algorithmic work: corpus + inverse norms once per scan launch, queries, results.
+  const double n = static_cast<double>(n_rows), d = e->dim, b = nq;
+  e->last_bytes = plan.size() * (n * d * 2.0 + n * 4.0) + b * d * 2.0 + b * k * 8.0;
+  e->last_flops = 2.0 * b * n * d;
+  e->have_timing = true;
+  return SA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sa_version(void) { return 100; }
+
+const char* sa_strerror(int rc) {
+  switch (rc) {
+    case SA_OK: return "ok";
+    case SA_ERR_CUDA: return "CUDA error";
+    case SA_ERR_ARG: return "bad argument";
+    case SA_ERR_COMM: return "collective error";
+    case SA_ERR_CAPACITY: return "capacity exceeded";
+    case SA_ERR_DEVICE: return "unsupported device (needs compute capability 10.x / sm_100a)";
+    default: return "unknown status";
+  }
+}
+
+const char* sa_last_error(void) { return g_err; }
+
+int sa_engine_create(sa_engine** out, int device, int dim, int64_t capacity_rows, int max_batch, int max_k) {
+  if (!out) return fail(SA_ERR_ARG, "null out");
+  *out = nullptr;
+  if (dim <= 0 || dim % 64 != 0) return fail(SA_ERR_ARG, "dim %d must be a positive multiple of 64", dim);
+  if (capacity_rows <= 0 || capacity_rows >= (1ll << 31) - 512)
+    return fail(SA_ERR_ARG, "capacity_rows %lld outside (0, 2^31-512)", (long long)capacity_rows);
+  if (max_batch <= 0) return fail(SA_ERR_ARG, "max_batch must be positive");
+  if (max_k <= 0 || max_k > SA_MAX_K) return fail(SA_ERR_ARG, "max_k %d outside [1, %d]", max_k, SA_MAX_K);
+  int ndev = 0;
+  SA_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(SA_ERR_ARG, "device %d not present (%d devices)", device, ndev);
+  cudaDeviceProp prop;
+  SA_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(SA_ERR_DEVICE, "device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major,
+                prop.minor);
+  SA_CUDA(cudaSetDevice(device));
+  if (!get_encode_fn()) return fail(SA_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+
+  sa_engine* e = new sa_engine();
+  e->device = device;
+  e->dim = dim;
+  e->capacity = capacity_rows;
+  e->max_batch = max_batch;
+  e->max_k = max_k;
+  e->num_sms = prop.multiProcessorCount;
+  const size_t part_elems = static_cast<size_t>(e->num_sms) * 128 * 32;
+  const size_t qelems = static_cast<size_t>(max_batch) * dim;
+  const size_t relems = static_cast<size_t>(max_batch) * max_k;
+  e->stage_rows = std::max<int64_t>(1, (64ll << 20) / (static_cast<int64_t>(dim) * 4));
+#define SA_TRY(call)                                                                                 \
+  do {                                                                                               \
+    cudaError_t _e = (call);                                                                         \
+    if (_e != cudaSuccess) {                                                                         \
+      fail(SA_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(_e));                             \
+      sa_engine_destroy(e);                                                                          \
+      return SA_ERR_CUDA;                                                                            \
+    }                                                                                                \
+  } while (0)
+  SA_TRY(cudaMalloc(&e->part_score, part_elems * sizeof(float)));
+  SA_TRY(cudaMalloc(&e->part_idx, part_elems * sizeof(int)));
+  SA_TRY(cudaMalloc(&e->q_bf16, qelems * 2));
+  SA_TRY(cudaMalloc(&e->q_f32, qelems * 4));
+  SA_TRY(cudaMalloc(&e->res_score, relems * 4));
+  SA_TRY(cudaMalloc(&e->res_idx, relems * 4));
+  SA_TRY(cudaMalloc(&e->d_stage, static_cast<size_t>(e->stage_rows) * dim * 4));
+  SA_TRY(cudaHostAlloc(&e->h_q, qelems * 4, cudaHostAllocDefault));
+  SA_TRY(cudaHostAlloc(&e->h_score, relems * 4, cudaHostAllocDefault));
+  SA_TRY(cudaHostAlloc(&e->h_idx, relems * 4, cudaHostAllocDefault));
+  SA_TRY(cudaHostAlloc(&e->h_stage, static_cast<size_t>(e->stage_rows) * dim * 4, cudaHostAllocDefault));
+  SA_TRY(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+  SA_TRY(cudaEventCreate(&e->ev_total[0]));
+  SA_TRY(cudaEventCreate(&e->ev_total[1]));
+  for (int i = 0; i < kMaxLaunches; ++i) {
+    e->ev_scan[i][0] = e->ev_scan[i][1] = nullptr;
+    SA_TRY(cudaEventCreate(&e->ev_scan[i][0]));
+    SA_TRY(cudaEventCreate(&e->ev_scan[i][1]));
+  }
+#undef SA_TRY
+  *out = e;
+  return SA_OK;
+}
+
+void sa_engine_destroy(sa_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  cudaFree(e->part_score);
+  cudaFree(e->part_idx);
+  cudaFree(e->q_bf16);
+  cudaFree(e->q_f32);
+  cudaFree(e->res_score);
+  cudaFree(e->res_idx);
+  cudaFree(e->d_stage);
+  cudaFreeHost(e->h_q);
+  cudaFreeHost(e->h_score);
+  cudaFreeHost(e->h_idx);
+  cudaFreeHost(e->h_stage);
+  if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  for (int i = 0; i < 2; ++i)
+    if (e->ev_total[i]) cudaEventDestroy(e->ev_total[i]);
+  for (int i = 0; i < kMaxLaunches; ++i)
+    for (int j = 0; j < 2; ++j)
+      if (e->ev_scan[i][j]) cudaEventDestroy(e->ev_scan[i][j]);
+  delete e;
+}
+
+int sa_corpus_bind(sa_engine* e, void* rows_bf16_dev, float* inv_norm_dev, int64_t n_valid) {
+  if (!e || !rows_bf16_dev || !inv_norm_dev) return fail(SA_ERR_ARG, "null argument");
+  if (reinterpret_cast<uintptr_t>(rows_bf16_dev) % 16) return fail(SA_ERR_ARG, "corpus must be 16-byte aligned");
+  if (n_valid < 0 || n_valid > e->capacity) return fail(SA_ERR_CAPACITY, "n_valid outside [0, capacity]");
+  SA_CUDA(cudaSetDevice(e->device));
+  int rc = encode_rows_map(&e->tmap_c[0], rows_bf16_dev, static_cast<uint64_t>(e->capacity), e->dim, sa::kBlockN);
+  if (rc) return rc;
+  rc = encode_rows_map(&e->tmap_c[1], rows_bf16_dev, static_cast<uint64_t>(e->capacity), e->dim, sa::kBlockN / 2);
+  if (rc) return rc;
+  e->corpus = static_cast<uint16_t*>(rows_bf16_dev);
+  e->inv_norm = inv_norm_dev;
+  e->n_rows = n_valid;
+  e->bound = true;
+  return SA_OK;
+}
+
+int sa_corpus_commit(sa_engine* e, int64_t first_row, int64_t n_new, uintptr_t stream) {
+  int rc = check_engine(e);
+  if (rc) return rc;
+  if (first_row != e->n_rows) return fail(SA_ERR_ARG, "commit must start at the current row count %lld", (long long)e->n_rows);
+  if (n_new < 0 || first_row + n_new > e->capacity) return fail(SA_ERR_CAPACITY, "commit past capacity");
+  if (n_new == 0) return SA_OK;
+  SA_CUDA(cudaSetDevice(e->device));
+  const long long threads = n_new * 32;
+  const int block = 256;
+  const long long grid = (threads + block - 1) / block;
+  sa::sa_rownorm_kernel<<<static_cast<unsigned>(grid), block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      e->corpus, e->inv_norm, first_row, n_new, e->dim);
+  SA_CUDA(cudaGetLastError());
+  e->n_rows = first_row + n_new;
+  return SA_OK;
+}
+
+int sa_corpus_append_f32(sa_engine* e, const float* rows_f32_dev, int64_t n_new, uintptr_t stream) {
+  int rc = check_engine(e);
+  if (rc) return rc;
+  if (!rows_f32_dev) return fail(SA_ERR_ARG, "null rows");
+  if (n_new < 0 || e->n_rows + n_new > e->capacity) return fail(SA_ERR_CAPACITY, "append past capacity");
+  if (n_new == 0) return SA_OK;
+  SA_CUDA(cudaSetDevice(e->device));
+  const long long threads = n_new * 32;
+  const int block = 256;
+  const long long grid = (threads + block - 1) / block;
+  sa::sa_convert_rows_kernel<<<static_cast<unsigned>(grid), block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      rows_f32_dev, e->corpus + e->n_rows * e->dim, e->inv_norm + e->n_rows, n_new, e->dim);
+  SA_CUDA(cudaGetLastError());
+  e->n_rows += n_new;
+  return SA_OK;
+}
+
+int sa_corpus_append_host_f32(sa_engine* e, const float* rows_f32_host, int64_t n_new) {
+  int rc = check_engine(e);
+  if (rc) return rc;
+  if (!rows_f32_host) return fail(SA_ERR_ARG, "null rows");
+  if (n_new < 0 || e->n_rows + n_new > e->capacity) return fail(SA_ERR_CAPACITY, "append past capacity");
+  SA_CUDA(cudaSetDevice(e->device));
+  int64_t done = 0;
+  while (done < n_new) {
+    const int64_t n = std::min(e->stage_rows, n_new - done);
+    const size_t bytes = static_cast<size_t>(n) * e->dim * 4;
+    memcpy(e->h_stage, rows_f32_host + done * e->dim, bytes);
+    SA_CUDA(cudaMemcpyAsync(e->d_stage, e->h_stage, bytes, cudaMemcpyHostToDevice, e->own_stream));
+    rc = sa_corpus_append_f32(e, e->d_stage, n, reinterpret_cast<uintptr_t>(e->own_stream));
+    if (rc) return rc;
+    SA_CUDA(cudaStreamSynchronize(e->own_stream));  // staging buffers are reused by the next chunk
+    done += n;
+  }
+  return SA_OK;
+}
+
+int sa_corpus_reset(sa_engine* e) {
+  if (!e) return fail(SA_ERR_ARG, "null engine");
+  e->n_rows = 0;
+  return SA_OK;
+}
+
+int64_t sa_corpus_rows(const sa_engine* e) { return e ? e->n_rows : -1; }
+
+int sa_search(sa_engine* e, const void* q_bf16_dev, int nq, int k, float* out_score_dev, int32_t* out_idx_dev,
+              double* out_score64_dev, uintptr_t stream) {
+  int rc = check_engine(e);
+  if (rc) return rc;
+  return do_search(e, static_cast<const uint16_t*>(q_bf16_dev), nq, k, out_score_dev, out_idx_dev, out_score64_dev,
+                   reinterpret_cast<cudaStream_t>(stream));
+}
+
+int sa_search_f32(sa_engine* e, const float* q_f32_dev, int nq, int k, float* out_score_dev, int32_t* out_idx_dev,
+                  double* out_score64_dev, uintptr_t stream) {
+  int rc = check_engine(e);
+  if (rc) return rc;
+  if (!q_f32_dev) return fail(SA_ERR_ARG, "null queries");
+  if (nq <= 0 || nq > e->max_batch) return fail(SA_ERR_CAPACITY, "nq %d outside [1, max_batch %d]", nq, e->max_batch);
+  SA_CUDA(cudaSetDevice(e->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long threads = static_cast<long long>(nq) * 32;
+  sa::sa_convert_rows_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(q_f32_dev, e->q_bf16,
+                                                                                         nullptr, nq, e->dim);
+  SA_CUDA(cudaGetLastError());
+  rc = do_search(e, e->q_bf16, nq, k, out_score_dev, out_idx_dev, out_score64_dev, st);
+  if (rc == SA_OK) e->last_kernels += 1;
+  return rc;
+}
+
+int sa_search_host(sa_engine* e, const float* q_f32_host, int nq, int k, float* out_score_host,
+                   int32_t* out_idx_host) {
+  int rc = check_engine(e);
+  if (rc) return rc;
+  if (!q_f32_host || !out_score_host || !out_idx_host) return fail(SA_ERR_ARG, "null buffer");
+  if (nq <= 0 || nq > e->max_batch) return fail(SA_ERR_CAPACITY, "nq %d outside [1, max_batch %d]", nq, e->max_batch);
+  if (k <= 0 || k > e->max_k) return fail(SA_ERR_ARG, "k %d outside [1, max_k %d]", k, e->max_k);
+  SA_CUDA(cudaSetDevice(e->device));
+  const size_t qbytes = static_cast<size_t>(nq) * e->dim * 4;
+  const size_t rbytes = static_cast<size_t>(nq) * k * 4;
+  memcpy(e->h_q, q_f32_host, qbytes);
+  SA_CUDA(cudaMemcpyAsync(e->q_f32, e->h_q, qbytes, cudaMemcpyHostToDevice, e->own_stream));
+  rc = sa_search_f32(e, e->q_f32, nq, k, e->res_score, e->res_idx, nullptr, reinterpret_cast<uintptr_t>(e->own_stream));
+  if (rc) return rc;
+  SA_CUDA(cudaMemcpyAsync(e->h_score, e->res_score, rbytes, cudaMemcpyDeviceToHost, e->own_stream));
+  SA_CUDA(cudaMemcpyAsync(e->h_idx, e->res_idx, rbytes, cudaMemcpyDeviceToHost, e->own_stream));
+  SA_CUDA(cudaStreamSynchronize(e->own_stream));
+  memcpy(out_score_host, e->h_score, rbytes);
+  memcpy(out_idx_host, e->h_idx, rbytes);
+  return SA_OK;
+}
+
+int sa_merge_shards(sa_engine* e, const double* score64_dev, const int64_t* global_idx_dev, int n_shards, int nq,
+                    int k, float* out_score_dev, int64_t* out_idx_dev, uintptr_t stream) {
+  if (!e || !score64_dev || !global_idx_dev || !out_score_dev || !out_idx_dev) return fail(SA_ERR_ARG, "null argument");
+  if (n_shards <= 0 || n_shards > 64) return fail(SA_ERR_ARG, "n_shards %d outside [1, 64]", n_shards);
+  if (nq <= 0 || k <= 0) return fail(SA_ERR_ARG, "nq and k must be positive");
+  SA_CUDA(cudaSetDevice(e->device));
+  sa::sa_merge_shards_kernel<<<(nq + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      score64_dev, reinterpret_cast<const long long*>(global_idx_dev), n_shards, nq, k, out_score_dev,
+      reinterpret_cast<long long*>(out_idx_dev));
+  SA_CUDA(cudaGetLastError());
+  return SA_OK;
+}
+
+int sa_last_timing(sa_engine* e, float* scan_ms, float* total_ms, double* bytes, double* flops, int* launches,
+                   int* kernels) {
+  if (!e) return fail(SA_ERR_ARG, "null engine");
+  if (!e->have_timing) return fail(SA_ERR_ARG, "no search has run on this engine");
+  SA_CUDA(cudaSetDevice(e->device));
+  SA_CUDA(cudaEventSynchronize(e->ev_total[1]));
+  float tot = 0.f, scan = 0.f;
+  SA_CUDA(cudaEventElapsedTime(&tot, e->ev_total[0], e->ev_total[1]));
+  for (int i = 0; i < e->last_launches; ++i) {
+    float ms = 0.f;
+    SA_CUDA(cudaEventElapsedTime(&ms, e->ev_scan[i][0], e->ev_scan[i][1]));
+    scan += ms;
+  }
+  if (scan_ms) *scan_ms = scan;
+  if (total_ms) *total_ms = tot;
+  if (bytes) *bytes = e->last_bytes;
+  if (flops) *flops = e->last_flops;
+  if (launches) *launches = e->last_launches;
+  if (kernels) *kernels = e->last_kernels;
+  return SA_OK;
+}
+
+int sa_set_option(sa_engine* e, const char* name, int64_t value) {
+  if (!e || !name) return fail(SA_ERR_ARG, "null argument");
+  if (!strcmp(name, "cta_group")) {
+    if (value < 0 || value > 2) return fail(SA_ERR_ARG, "cta_group must be 0, 1 or 2");
+    e->opt_cta_group = static_cast<int>(value);
+    return SA_OK;
+  }
+  if (!strcmp(name, "max_launch_qblocks")) {
+    if (value < 0) return fail(SA_ERR_ARG, "max_launch_qblocks must be >= 0");
+    e->opt_max_launch_qblocks = static_cast<int>(value);
+    return SA_OK;
+  }
+  return fail(SA_ERR_ARG, "unknown option '%s'", name);
+}
+
+int sa_get_info(const sa_engine* e, const char* name, int64_t* value) {
+  if (!e || !name || !value) return fail(SA_ERR_ARG, "null argument");
+  if (!strcmp(name, "num_sms")) *value = e->num_sms;
+  else if (!strcmp(name, "dim")) *value = e->dim;
+  else if (!strcmp(name, "capacity")) *value = e->capacity;
+  else if (!strcmp(name, "n_rows")) *value = e->n_rows;
+  else if (!strcmp(name, "max_batch")) *value = e->max_batch;
+  else if (!strcmp(name, "max_k")) *value = e->max_k;
+  else return fail(SA_ERR_ARG, "unknown info '%s'", name);
+  return SA_OK;
+}
+
+int sa_debug_tile_dots(sa_engine* e, const void* q_bf16_dev, int nq, int tile, int cta_group, float* out_dots_dev,
+                       uintptr_t stream) {
+  int rc = check_engine(e);
+  if (rc) return rc;
+  if (!q_bf16_dev || !out_dots_dev) return fail(SA_ERR_ARG, "null buffer");
+  if (cta_group != 1 && cta_group != 2) return fail(SA_ERR_ARG, "cta_group must be 1 or 2");
+  const int num_tiles = static_cast<int>((e->n_rows + sa::kBlockN - 1) / sa::kBlockN);
+  if (tile < 0 || tile >= num_tiles) return fail(SA_ERR_ARG, "tile %d outside [0, %d)", tile, num_tiles);
+  const int rows_per_qb = 128 * cta_group;
+  const int nqb = (nq + rows_per_qb - 1) / rows_per_qb;
+  if (nq <= 0 || nqb * cta_group > e->num_sms) return fail(SA_ERR_CAPACITY, "nq too large for the debug hook");
+  SA_CUDA(cudaSetDevice(e->device));
+  CUtensorMap tq;
+  rc = encode_rows_map(&tq, q_bf16_dev, static_cast<uint64_t>(nq), e->dim, sa::kBlockM);
+  if (rc) return rc;
+  sa::ScanParams sp = {};
+  sp.inv_norm = e->inv_norm;
+  sp.n_rows = e->n_rows;
+  sp.nq = nq;
+  sp.num_kb = e->dim / sa::kBlockK;
+  sp.num_tiles = num_tiles;
+  sp.nqb = nqb;
+  sp.tl_count = 1;  // one tile lane: every unit walks all tiles, dumps `tile`
+  sp.part_score = e->part_score;
+  sp.part_idx = e->part_idx;
+  sp.corpus_evict_first = 0;
+  sp.dbg_dots = out_dots_dev;
+  sp.dbg_tile = tile;
+  return launch_scan_dispatch(cta_group, 16, true, tq, e->tmap_c[cta_group - 1], sp, nqb * cta_group,
+                              reinterpret_cast<cudaStream_t>(stream));
+}
+
+int sa_host_alloc(void** out, uint64_t bytes) {
+  if (!out) return fail(SA_ERR_ARG, "null out");
+  SA_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+  return SA_OK;
+}
+
+int sa_host_free(void* p) {
+  SA_CUDA(cudaFreeHost(p));
+  return SA_OK;
+}
+
+}  // extern "C"
