@@ -194,9 +194,12 @@ def cosine_topk_fast(q_bits: np.ndarray, c_chunks, k: int, margin: int = 32):
     cand_s = np.full((nq, keep), -np.inf, dtype=np.float32)
     cand_i = np.full((nq, keep), -1, dtype=np.int64)
     cand_bits = np.zeros((nq, keep, q.shape[1]), dtype=np.uint16)
+    first_rows: list[int] = []  # first k rows with a non-zero norm (the answer for an all-zero query)
     for lo, bits in c_chunks:
         c = bf16_bits_to_f32(bits)
         cn = np.sqrt(np.einsum("ij,ij->i", c, c, dtype=np.float32))
+        if len(first_rows) < k:
+            first_rows.extend((np.flatnonzero(bits.any(axis=1))[: k - len(first_rows)] + lo).tolist())
         inv = np.where(cn > 0, 1.0 / np.where(cn > 0, cn, 1), 0).astype(np.float32)
         s = (qh @ c.T) * inv[None, :]
         s[:, cn == 0] = -np.inf
@@ -214,6 +217,8 @@ def cosine_topk_fast(q_bits: np.ndarray, c_chunks, k: int, margin: int = 32):
     out_s = np.full((nq, k), -np.inf)
     out_i = np.full((nq, k), -1, dtype=np.int64)
     for r in range(nq):
+        if qn[r] == 0:  # all-zero query: every eligible row scores 0, lowest rows win (handled below)
+            continue
         ok = cand_i[r] >= 0
         if not ok.any():
             continue
@@ -223,6 +228,9 @@ def cosine_topk_fast(q_bits: np.ndarray, c_chunks, k: int, margin: int = 32):
         ts, ti = _select_topk(s64[fin], rows[fin], k)
         out_s[r, : len(ts)] = ts
         out_i[r, : len(ti)] = ti
+    for r in np.flatnonzero(qn == 0):
+        out_s[r, : len(first_rows)] = 0.0
+        out_i[r, : len(first_rows)] = first_rows
     return out_s, out_i
 
 

@@ -202,8 +202,7 @@ int choose_cg(const sa_engine* e, int nq) {
   if (e->opt_cta_group == 1 || e->opt_cta_group == 2) return e->opt_cta_group;
   // Auto: a CTA pair shares the corpus tile between two query blocks (half the smem/L2 operand traffic per
   // flop), which pays once the batch fills 256-row pair blocks; small batches are HBM-bound and use 1 CTA.
-  (void)nq;
-  return 1;  // TODO(round 1): flip to `nq > 128 ? 2 : 1` once the pair kernel is validated on hardware
+  return nq > 128 ? 2 : 1;
 }
 
 int check_engine(const sa_engine* e) {

@@ -1,0 +1,221 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (ctypes), against the CPU oracle on the same
+seeded inputs.  Index lists must be equal element for element (integer work: bit-exact); scores are float32
+roundings of float64 cosines and must agree within 1e-6 (north_star allows 1e-3).
+
+Run on a B200 with:  python -m pytest tests -m gpu
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SCORE_TOL = 1e-6
+
+
+def dev(bits):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(bits).view(np.int16)).view(torch.bfloat16).cuda()
+
+
+def check(ix, q_bits, c_bits, k, cg=None):
+    import torch
+    from oracle import bruteforce as bf
+    if cg is not None:
+        ix.set_option("cta_group", cg)
+    s, i = ix.search(dev(q_bits), k)
+    torch.cuda.synchronize()
+    rs, ri = bf.cosine_topk_f64(q_bits, c_bits, k)
+    got_i, got_s = i.cpu().numpy(), s.cpu().numpy()
+    assert (got_i == ri).all(), bf.compare_topk(got_i, got_s, ri, rs)
+    fin = np.isfinite(rs)
+    assert (np.isneginf(got_s) == ~fin).all()
+    if fin.any():
+        assert np.abs(got_s.astype(np.float64) - rs)[fin].max() < SCORE_TOL
+    return got_s, got_i
+
+
+@pytest.fixture(scope="module")
+def bf():
+    from oracle import bruteforce
+    return bruteforce
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("n,dim,nq,k", [
+    (20000, 1536, 200, 10),    # Lab2 shape: ragged last query block, 79 tiles (last one partial)
+    (5000, 768, 37, 5),        # config-5 shape (768-d, top-5)
+    (256, 64, 1, 1),           # one tile, one query
+    (257, 128, 129, 3),        # one row into the second tile; one query into the second block
+    (70000, 256, 300, 12),     # more tiles than tile lanes; k at the 16-entry list limit (k + 4)
+    (9000, 192, 64, 28),       # 32-entry candidate lists, SA_MAX_K
+])
+def test_search_matches_oracle(bf, cg, n, dim, nq, k):
+    from qsa_b200.engine import VectorIndex
+    c = bf.synth_rows(1234, 0, n, dim)
+    q = bf.synth_queries(4321, nq, dim, c)
+    ix = VectorIndex(dim=dim, capacity=n + 513, max_batch=512, max_k=28)
+    ix.append_bf16_bits(c)
+    check(ix, q, c, k, cg)
+    ix.close()
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+def test_ties_zero_rows_zero_queries_and_short_corpus(bf, cg):
+    from qsa_b200.engine import VectorIndex
+    dim, n = 128, 1000
+    c = bf.synth_rows(5, 0, n, dim)
+    c[700] = c[3]; c[701] = c[3]; c[2] = c[3]      # exact duplicates -> ties broken by ascending row
+    c[11] = 0; c[999] = 0                          # all-zero rows are never returned
+    c[500] = bf.f32_to_bf16_bits(bf.bf16_bits_to_f32(c[40]) * 2)   # scaled copy: same cosine as row 40
+    q = bf.synth_queries(6, 20, dim, c)
+    q[0] = c[3]
+    q[1] = c[40]
+    q[2] = 0                                       # all-zero query: score 0 everywhere, lowest rows win
+    ix = VectorIndex(dim=dim, capacity=2048, max_batch=128, max_k=28)
+    ix.append_bf16_bits(c)
+    s, i = check(ix, q, c, 10, cg)
+    assert i[0, :4].tolist() == [2, 3, 700, 701]
+    assert set(i[1, :2].tolist()) == {40, 500} and i[1, 0] == 40
+    assert i[2].tolist() == [0, 1, 2, 3, 4, 5, 6, 7, 8, 9] and (s[2] == 0).all()
+    # corpus shorter than k: unused slots are (-inf, -1)
+    ix2 = VectorIndex(dim=dim, capacity=256, max_batch=128, max_k=28)
+    ix2.append_bf16_bits(c[:12])                   # 11 eligible rows (row 11 is zero)
+    s2, i2 = check(ix2, q[:5], c[:12], 20, cg)
+    assert (i2[:, 11:] == -1).all()
+    ix.close(); ix2.close()
+
+
+def test_empty_corpus_returns_no_rows(bf):
+    import torch
+    from qsa_b200.engine import VectorIndex
+    ix = VectorIndex(dim=64, capacity=512, max_batch=128, max_k=10)
+    q = bf.synth_rows(1, 0, 3, 64)
+    s, i = ix.search(dev(q), 4)
+    torch.cuda.synchronize()
+    assert (i.cpu().numpy() == -1).all() and np.isneginf(s.cpu().numpy()).all()
+    ix.close()
+
+
+def test_streaming_epochs_search_sees_committed_prefix(bf):
+    """Append-while-serving (LAB2-Walkthrough.md:41-51 ingest half): every search sees exactly the committed
+    prefix; rows written but not yet committed are invisible; reset() empties the index."""
+    from qsa_b200.engine import VectorIndex
+    dim = 256
+    c = bf.synth_rows(77, 0, 3000, dim)
+    q = bf.synth_queries(78, 50, dim, c)
+    ix = VectorIndex(dim=dim, capacity=4096, max_batch=128, max_k=10)
+    import torch
+    ix.rows[:3000].copy_(dev(c))                   # all bytes are already in HBM ...
+    done = 0
+    for step in (300, 212, 1, 999, 1488):          # ... but only committed rows may be returned
+        ix.commit(done, step)
+        done += step
+        assert len(ix) == done
+        check(ix, q, c[:done], 10)
+    ix.reset()
+    assert len(ix) == 0
+    ix.append_bf16_bits(c[:100])
+    check(ix, q[:7], c[:100], 10)
+    ix.close()
+
+
+def test_fp32_ingest_and_host_path_round_like_the_oracle(bf):
+    """fp32 embeddings (ARRAY<FLOAT>, main.tf:141,215) are rounded to bf16 (RNE) on the device exactly as the
+    oracle rounds them; sa_search_host (host buffers) equals the device path."""
+    import torch
+    from qsa_b200.engine import VectorIndex
+    dim, n, nq, k = 1536, 6000, 150, 10
+    g = np.random.default_rng(3)
+    cf = g.standard_normal((n, dim), dtype=np.float32) * np.exp(g.uniform(-1, 1, (n, 1))).astype(np.float32)
+    qf = g.standard_normal((nq, dim), dtype=np.float32)
+    qf[1::2] = cf[(np.arange(1, nq, 2) * 37) % n] + 0.3 * g.standard_normal((nq // 2, dim), dtype=np.float32)
+    c, q = bf.f32_to_bf16_bits(cf), bf.f32_to_bf16_bits(qf)
+    ix = VectorIndex(dim=dim, capacity=8192, max_batch=256, max_k=10)
+    ix.append(cf[:2500])                           # host fp32 -> pinned staging -> device convert
+    ix.append(torch.from_numpy(cf[2500:]).cuda())  # device fp32
+    assert (ix.rows[:n].view(torch.int16).cpu().numpy().view(np.uint16) == c).all()
+    rs, ri = bf.cosine_topk_f64(q, c, k)
+    s, i = ix.search(torch.from_numpy(qf).cuda(), k)     # fp32 device queries
+    torch.cuda.synchronize()
+    assert (i.cpu().numpy() == ri).all()
+    hs, hi = ix.search_host(qf, k)                       # host fp32 queries, host results
+    assert (hi == ri).all() and np.abs(hs.astype(np.float64) - rs).max() < SCORE_TOL
+    t = ix.last_timing()
+    assert t.launches >= 1 and t.kernels >= 3 and t.scan_ms > 0 and t.flops == 2.0 * nq * n * dim
+    ix.close()
+
+
+def test_batch_larger_than_one_launch_and_launch_split(bf):
+    """Batches beyond one wave of query blocks are split into several scan launches; forcing small launches
+    must not change the answer."""
+    from qsa_b200.engine import VectorIndex
+    dim, n, nq, k = 128, 30000, 1100, 10
+    c = bf.synth_rows(21, 0, n, dim)
+    q = bf.synth_queries(22, nq, dim, c)
+    ix = VectorIndex(dim=dim, capacity=n, max_batch=2048, max_k=10)
+    ix.append_bf16_bits(c)
+    for cg in (1, 2):
+        check(ix, q, c, k, cg)
+    ix.set_option("max_launch_qblocks", 2)
+    for cg in (1, 2):
+        check(ix, q, c, k, cg)
+    assert ix.last_timing().launches == 3          # 1100 queries / (2 pair blocks x 256)
+    ix.close()
+
+
+def test_merge_shards_equals_global(bf):
+    """Row-sharded search on one GPU (4 engines), device merge kernel vs the unsharded oracle."""
+    import torch
+    from qsa_b200.engine import VectorIndex
+    dim, n, nq, k = 256, 12000, 140, 10
+    c = bf.synth_rows(31, 0, n, dim)
+    c[9000] = c[10]                                # a tie across shards: the lower global row must win
+    q = bf.synth_queries(32, nq, dim, c)
+    q[0] = c[10]
+    cuts = [0, 2500, 6000, 9500, n]
+    ss, ii = [], []
+    keep = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        ix = VectorIndex(dim=dim, capacity=b - a, max_batch=256, max_k=10)
+        ix.append_bf16_bits(c[a:b])
+        s, i, s64 = ix.search(dev(q), k, want_score64=True)
+        ss.append(s64)
+        ii.append(torch.where(i >= 0, i.to(torch.int64) + a, torch.full_like(i, -1, dtype=torch.int64)))
+        keep.append(ix)
+    fs, fi = keep[0].merge_shards(torch.stack(ss), torch.stack(ii))
+    torch.cuda.synchronize()
+    rs, ri = bf.cosine_topk_f64(q, c, k)
+    assert (fi.cpu().numpy() == ri).all()
+    assert fi[0, 0].item() == 10 and fi[0, 1].item() == 9000
+    assert np.abs(fs.cpu().numpy().astype(np.float64) - rs).max() < SCORE_TOL
+    for ix in keep:
+        ix.close()
+
+
+def test_full_size_properties_1M(bf):
+    """Config 2 scale (1M x 1536, batch 256, top-10) through size-independent properties:
+    planted queries return their planted row first; results are sorted; a sample of queries is checked against
+    the oracle over all rows; searching the two halves and merging equals searching the whole."""
+    import torch
+    from qsa_b200.engine import VectorIndex
+    dim, n, nq, k = 1536, 1_000_000, 256, 10
+    ix = VectorIndex(dim=dim, capacity=n, max_batch=256, max_k=10)
+    chunks = []
+    for ci in range((n + bf.CHUNK_ROWS - 1) // bf.CHUNK_ROWS):
+        m = min(bf.CHUNK_ROWS, n - ci * bf.CHUNK_ROWS)
+        bits = bf.synth_rows(1234, ci, m, dim)
+        ix.append_bf16_bits(bits)
+        chunks.append((ci * bf.CHUNK_ROWS, bits))
+    q = bf.synth_queries(4321, nq, dim, chunks[0][1])
+    s, i, s64 = ix.search(dev(q), k, want_score64=True)
+    torch.cuda.synchronize()
+    gi, gs = i.cpu().numpy(), s.cpu().numpy()
+    for r in range(1, nq, 2):
+        assert gi[r, 0] == bf.planted_row(r, len(chunks[0][1]))
+    assert (np.diff(s64.cpu().numpy(), axis=1) <= 0).all()
+    assert (gi >= 0).all() and all(len(set(row)) == k for row in gi.tolist())
+    sample = np.arange(0, nq, 16)
+    rs, ri = bf.cosine_topk_fast(q[sample], chunks, k)
+    assert (gi[sample] == ri).all()
+    assert np.abs(gs[sample].astype(np.float64) - rs).max() < SCORE_TOL
+    ix.close()
