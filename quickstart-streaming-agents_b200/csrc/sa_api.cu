@@ -358,7 +358,8 @@ int sa_engine_create(sa_engine** out, int device, int dim, int64_t capacity_rows
   SA_TRY(cudaHostAlloc(&e->h_score, relems * 4, cudaHostAllocDefault));
   SA_TRY(cudaHostAlloc(&e->h_idx, relems * 4, cudaHostAllocDefault));
   SA_TRY(cudaHostAlloc(&e->h_stage, static_cast<size_t>(e->stage_rows) * dim * 4, cudaHostAllocDefault));
-  SA_TRY(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+  // a blocking stream: ordered after work already queued on the legacy default stream (torch's default)
+  SA_TRY(cudaStreamCreate(&e->own_stream));
   SA_TRY(cudaEventCreate(&e->ev_total[0]));
   SA_TRY(cudaEventCreate(&e->ev_total[1]));
   for (int i = 0; i < kMaxLaunches; ++i) {

@@ -94,6 +94,7 @@ class VectorIndex:
         else:
             x = np.ascontiguousarray(rows_f32, dtype=np.float32)
             assert x.ndim == 2 and x.shape[1] == self.dim
+            torch.cuda.current_stream(self.device).synchronize()  # the *_host calls run on the engine's stream
             capi.check(self.lib.sa_corpus_append_host_f32(self._h, x.ctypes.data, x.shape[0]),
                        "sa_corpus_append_host_f32")
         return first
@@ -111,6 +112,14 @@ class VectorIndex:
         self.rows[first:first + n].copy_(src)
         self.commit(first, n)
         return first
+
+    def delete_rows(self, rows) -> None:
+        """Tombstone rows: zero the stored vector and its inverse norm -- all-zero rows are never returned."""
+        if len(rows) == 0:
+            return
+        ix = torch.as_tensor(list(rows), dtype=torch.long, device=self.rows.device)
+        self.rows.index_fill_(0, ix, 0)
+        self.inv_norm.index_fill_(0, ix, 0)
 
     def commit(self, first: int, n: int) -> None:
         """Rows [first, first+n) were written into ``self.rows`` in place: compute norms and publish them."""
@@ -146,6 +155,7 @@ class VectorIndex:
         nq = q.shape[0]
         score = np.empty((nq, k), dtype=np.float32)
         idx = np.empty((nq, k), dtype=np.int32)
+        torch.cuda.current_stream(self.device).synchronize()  # the *_host calls run on the engine's stream
         capi.check(self.lib.sa_search_host(self._h, q.ctypes.data, nq, k, score.ctypes.data, idx.ctypes.data),
                    "sa_search_host")
         return score, idx

@@ -1,0 +1,127 @@
+"""VECTOR_SEARCH_AGG drop-in.
+
+Reference statement (terraform/lab2-vector-search/main.tf:292)::
+
+    SELECT qe.query, vs.search_results[1].document_id AS document_id_1, vs.search_results[1].chunk AS chunk_1,
+           vs.search_results[1].score AS score_1, ... [2] ..., ... [3] ...
+    FROM queries_embed AS qe,
+         LATERAL TABLE(VECTOR_SEARCH_AGG(documents_vectordb_lab2, DESCRIPTOR(embedding), qe.embedding, 3)) AS vs
+
+``VectorTable`` is the external table ``documents_vectordb_lab2 (document_id STRING, chunk STRING, embedding
+ARRAY<FLOAT>)`` (main.tf:215; Lab4 adds metadata columns, terraform/lab4-pubsec-fraud-agents/main.tf:271-289):
+the embedding column lives in HBM inside a ``VectorIndex``, the other columns in a host side table.
+``vector_search_agg(table, "embedding", query_vectors, k)`` returns, per query, the 1-indexed
+``search_results`` array of rows ``(table columns..., score)`` in descending score order.
+
+The index object only needs ``append(rows_f32) -> first_row``, ``search_host(q_f32, k) -> (score, idx)``,
+``reset()``, ``__len__`` and ``delete_rows`` -- production passes ``engine.VectorIndex`` (CUDA, no fallback).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+
+@dataclass
+class SearchHit:
+    document_id: str | None
+    chunk: str | None
+    score: float
+    row: int
+    metadata: dict = field(default_factory=dict)
+
+
+class VectorTable:
+    def __init__(self, index, name: str = "documents_vectordb_lab2", embedding_column: str = "embedding"):
+        self.index = index
+        self.name = name
+        self.embedding_column = embedding_column
+        self.document_id: list[str | None] = []
+        self.chunk: list[str | None] = []
+        self.metadata: list[dict] = []
+        self._row_of: dict[str, int] = {}
+
+    def __len__(self) -> int:
+        return len(self.document_id)
+
+    def upsert_many(self, document_ids, chunks, embeddings: np.ndarray, metadata=None) -> None:
+        """Insert rows; a document_id seen before replaces its old row (sink-connector upsert semantics): the
+        old row's vector is zeroed, and all-zero rows are never returned by the engine."""
+        embeddings = np.ascontiguousarray(embeddings, dtype=np.float32)
+        n = len(document_ids)
+        assert embeddings.shape[0] == n and len(chunks) == n
+        metadata = metadata or [{} for _ in range(n)]
+        stale = [self._row_of[d] for d in document_ids if d is not None and d in self._row_of]
+        # a document repeated inside this very batch: keep its last occurrence only
+        last = {d: i for i, d in enumerate(document_ids) if d is not None}
+        keep = [i for i, d in enumerate(document_ids) if d is None or last[d] == i]
+        if stale:
+            self.index.delete_rows(stale)
+        first = self.index.append(embeddings[keep])
+        assert first == len(self.document_id), "side table and index out of step"
+        for j, i in enumerate(keep):
+            self.document_id.append(document_ids[i])
+            self.chunk.append(chunks[i])
+            self.metadata.append(metadata[i])
+            if document_ids[i] is not None:
+                self._row_of[document_ids[i]] = first + j
+
+    def clear(self) -> None:
+        """What scripts/common/clear_mongodb.py:98-158 does before a re-publish."""
+        self.index.reset()
+        self.document_id.clear()
+        self.chunk.clear()
+        self.metadata.clear()
+        self._row_of.clear()
+
+
+def vector_search_agg(table: VectorTable, descriptor: str, query_vectors: np.ndarray, k: int) -> list[list[SearchHit]]:
+    """VECTOR_SEARCH_AGG(table, DESCRIPTOR(descriptor), query_vector, k) for a batch of query vectors."""
+    if descriptor != table.embedding_column:
+        raise ValueError(f"table {table.name} has no vector column {descriptor!r}")
+    q = np.ascontiguousarray(query_vectors, dtype=np.float32)
+    if q.ndim == 1:
+        q = q[None, :]
+    if q.shape[0] == 0:
+        return []
+    score, idx = table.index.search_host(q, k)
+    out = []
+    for r in range(q.shape[0]):
+        hits = []
+        for s, i in zip(score[r].tolist(), idx[r].tolist()):
+            if i < 0:
+                break
+            hits.append(SearchHit(table.document_id[i], table.chunk[i], float(s), int(i), table.metadata[i]))
+        out.append(hits)
+    return out
+
+
+def flatten_search_results(query: str | None, hits: list[SearchHit], n: int = 3) -> dict:
+    """The projection of main.tf:292: query + document_id_i / chunk_i / score_i for i = 1..n (null-padded)."""
+    rec = {"query": query}
+    for i in range(1, n + 1):
+        h = hits[i - 1] if i <= len(hits) else None
+        rec[f"document_id_{i}"] = h.document_id if h else None
+        rec[f"chunk_{i}"] = h.chunk if h else None
+        rec[f"score_{i}"] = h.score if h else None
+    return rec
+
+
+def rag_prompt(rec: dict) -> str:
+    """The CONCAT(...) of main.tf:331, character for character (SQL '' -> ', \\n -> newline)."""
+    def s(v):
+        return "" if v is None else str(v)
+    return (
+        "Based on the following search results, provide a helpful and comprehensive response to the user query "
+        "based upon the relevant retrieved documents. Cite the exact parts of the retrieved documents whenever "
+        "possible.\n\nUSER QUERY: " + s(rec["query"]) + "\n\nSEARCH RESULTS:\n\n"
+        "Document 1 (Similarity Score: " + s(rec["score_1"]) + "):\nSource: " + s(rec["document_id_1"]) +
+        "\nContent: " + s(rec["chunk_1"]) +
+        "\n\nDocument 2 (Similarity Score: " + s(rec["score_2"]) + "):\nSource: " + s(rec["document_id_2"]) +
+        "\nContent: " + s(rec["chunk_2"]) +
+        "\n\nDocument 3 (Similarity Score: " + s(rec["score_3"]) + "):\nSource: " + s(rec["document_id_3"]) +
+        "\nContent: " + s(rec["chunk_3"]) +
+        "\n\nINSTRUCTIONS:\n- Synthesize information from the most relevant documents above\n"
+        "- Provide specific, actionable guidance when possible\n- Reference document sources in your response\n"
+        "- If the search results don't contain relevant information, say so clearly\n\nRESPONSE:")

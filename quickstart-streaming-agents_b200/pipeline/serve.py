@@ -1,0 +1,208 @@
+"""Local serve loop for the Lab2 RAG pipeline.
+
+What Confluent Cloud Flink runs as continuous statements, this process runs as consumer/producer stages over
+topics with the same names and Avro schemas:
+
+  documents        --embed(stub)-->  documents_embed  --sink-->  VectorTable (HBM)         LAB2-Walkthrough.md:41-51
+  queries          --embed(stub)-->  queries_embed                                          main.tf:253
+  queries_embed    --VECTOR_SEARCH_AGG(table, DESCRIPTOR(embedding), embedding, k)-->  search_results   main.tf:292
+  search_results   --RAG prompt + generator(stub)-->  search_results_response              main.tf:331
+
+Records on ``queries_embed`` / ``documents_embed`` may also come from outside (pre-computed embeddings).
+Delivery is at-least-once: each stage commits its consumer offsets after its outputs are flushed.
+A poison record (bad magic byte, truncated Avro, wrong embedding length) is quarantined to ``<topic>.dlq``
+with the error text in its key, and the stage moves on.
+"""
+from __future__ import annotations
+
+import logging
+import time
+
+import numpy as np
+
+from ..embed.stub import StubEmbedder
+from ..operator import VectorTable, flatten_search_results, rag_prompt, vector_search_agg
+from ..transport.filelog import Consumer, Producer
+from ..wire import avro, schemas
+from ..wire.registry import SchemaRegistry
+
+log = logging.getLogger(__name__)
+
+
+def stub_generator(prompt: str, rec: dict) -> str:
+    """Stand-in for ml_predict('llm_textgen_model', prompt) (main.tf:331): a deterministic extractive answer that
+    cites the retrieved sources, so the test shape "response is non-empty" (testing/e2e/test_lab2.py:112-135) and
+    a human reading the topic both get something sensible."""
+    parts = []
+    for i in (1, 2, 3):
+        if rec.get(f"document_id_{i}") is not None:
+            chunk = (rec.get(f"chunk_{i}") or "").strip().replace("\n", " ")
+            parts.append(f"[{rec[f'document_id_{i}']}] (score {rec[f'score_{i}']:.4f}): {chunk[:240]}")
+    if not parts:
+        return "The search results don't contain relevant information for this query."
+    return "Based on the retrieved documents:\n" + "\n".join(parts)
+
+
+class Codec:
+    """Avro + Confluent framing for one log directory (schema ids from the registry stub)."""
+
+    def __init__(self, log_dir: str):
+        self.registry = SchemaRegistry(log_dir)
+        self._ids: dict[str, int] = {}
+
+    def schema_id(self, topic: str) -> int:
+        if topic not in self._ids:
+            self._ids[topic] = self.registry.register(f"{topic}-value", schemas.TOPIC_SCHEMAS[topic])
+        return self._ids[topic]
+
+    def encode(self, topic: str, record: dict) -> bytes:
+        return avro.frame(self.schema_id(topic), avro.encode(schemas.TOPIC_SCHEMAS[topic], record))
+
+    def decode(self, raw: bytes) -> dict:
+        sid, body = avro.unframe(raw)
+        return avro.decode(self.registry.get(sid), body)
+
+
+class Lab2Pipeline:
+    def __init__(self, log_dir: str, table: VectorTable, embedder=None, k: int = 3, max_batch: int = 1024,
+                 group: str = "sa-lab2", generator=stub_generator):
+        self.log_dir = log_dir
+        self.table = table
+        self.embedder = embedder or StubEmbedder(table.index.dim)
+        self.k = k
+        self.max_batch = max_batch
+        self.generator = generator
+        self.codec = Codec(log_dir)
+        self.producer = Producer({"log.dir": log_dir})
+        conf = {"log.dir": log_dir, "group.id": group, "auto.offset.reset": "earliest", "enable.auto.commit": False}
+        self.consumers = {}
+        for t in ("documents", "documents_embed", "queries", "queries_embed", "search_results"):
+            c = Consumer(conf)
+            c.subscribe([t])
+            self.consumers[t] = c
+        self.stats = {"documents": 0, "queries": 0, "searches": 0, "responses": 0, "quarantined": 0,
+                      "search_seconds": 0.0}
+
+    # ------------------------------------------------------------------ helpers
+    def _decode_all(self, topic: str, msgs):
+        good = []
+        for m in msgs:
+            try:
+                good.append((m, self.codec.decode(m.value())))
+            except Exception as e:  # poison message: quarantine, keep going
+                self.stats["quarantined"] += 1
+                log.warning("quarantined %s[%d]@%d: %s", topic, m.partition(), m.offset(), e)
+                self.producer.produce(f"{topic}.dlq", key=str(e), value=m.value())
+        return good
+
+    def _drain(self, topic: str):
+        c = self.consumers[topic]
+        msgs = c.consume(self.max_batch, 0.0)
+        return c, msgs, self._decode_all(topic, msgs)
+
+    def _check_vec(self, topic, m, vec):
+        dim = self.table.index.dim
+        if vec is None or len(vec) != dim or not np.isfinite(vec).all():
+            self.stats["quarantined"] += 1
+            why = f"embedding must be {dim} finite floats"
+            log.warning("quarantined %s@%d: %s", topic, m.offset(), why)
+            self.producer.produce(f"{topic}.dlq", key=why, value=m.value())
+            return False
+        return True
+
+    # ------------------------------------------------------------------ stages
+    def stage_documents(self) -> int:
+        c, msgs, recs = self._drain("documents")
+        for m, r in recs:
+            text = r.get("document_text") or ""
+            vec = self.embedder.embed(text)
+            self.producer.produce("documents_embed", key=m.key(), value=self.codec.encode(
+                "documents_embed", {"document_id": r.get("document_id"), "chunk": text, "embedding": vec}))
+        if msgs:
+            self.producer.flush()
+            c.commit()
+        return len(msgs)
+
+    def stage_sink(self) -> int:
+        c, msgs, recs = self._drain("documents_embed")
+        ids, chunks, vecs = [], [], []
+        for m, r in recs:
+            vec = r.get("embedding")
+            if not self._check_vec("documents_embed", m, vec):
+                continue
+            ids.append(r.get("document_id"))
+            chunks.append(r.get("chunk"))
+            vecs.append(vec)
+        if ids:
+            self.table.upsert_many(ids, chunks, np.stack(vecs))
+            self.stats["documents"] += len(ids)
+        if msgs:
+            self.producer.flush()
+            c.commit()
+        return len(msgs)
+
+    def stage_queries(self) -> int:
+        c, msgs, recs = self._drain("queries")
+        for m, r in recs:
+            q = r.get("query") or ""
+            self.producer.produce("queries_embed", value=self.codec.encode(
+                "queries_embed", {"query": q, "embedding": self.embedder.embed(q)}))
+        if msgs:
+            self.stats["queries"] += len(recs)
+            self.producer.flush()
+            c.commit()
+        return len(msgs)
+
+    def stage_search(self) -> int:
+        c, msgs, recs = self._drain("queries_embed")
+        texts, vecs = [], []
+        for m, r in recs:
+            vec = r.get("embedding")
+            if not self._check_vec("queries_embed", m, vec):
+                continue
+            texts.append(r.get("query"))
+            vecs.append(vec)
+        if vecs:
+            t0 = time.perf_counter()
+            hits = vector_search_agg(self.table, self.table.embedding_column, np.stack(vecs), self.k)
+            self.stats["search_seconds"] += time.perf_counter() - t0
+            for q, h in zip(texts, hits):
+                self.producer.produce("search_results", value=self.codec.encode(
+                    "search_results", flatten_search_results(q, h, schemas.RESULTS_PER_QUERY)))
+            self.stats["searches"] += len(vecs)
+        if msgs:
+            self.producer.flush()
+            c.commit()
+        return len(msgs)
+
+    def stage_response(self) -> int:
+        c, msgs, recs = self._drain("search_results")
+        for m, r in recs:
+            out = dict(r)
+            out["response"] = self.generator(rag_prompt(r), r)
+            self.producer.produce("search_results_response", value=self.codec.encode("search_results_response", out))
+            self.stats["responses"] += 1
+        if msgs:
+            self.producer.flush()
+            c.commit()
+        return len(msgs)
+
+    # ------------------------------------------------------------------ loop
+    def run_once(self) -> int:
+        """One pass over all stages in topological order; returns the number of records moved."""
+        return (self.stage_documents() + self.stage_sink() + self.stage_queries() + self.stage_search() +
+                self.stage_response())
+
+    def run_until_idle(self, max_passes: int = 1000) -> int:
+        total = 0
+        for _ in range(max_passes):
+            n = self.run_once()
+            total += n
+            if n == 0:
+                break
+        return total
+
+    def run_forever(self, idle_sleep: float = 0.05, stop=lambda: False) -> None:
+        while not stop():
+            if self.run_once() == 0:
+                time.sleep(idle_sleep)
