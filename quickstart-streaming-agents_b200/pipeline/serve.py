@@ -189,9 +189,16 @@ class Lab2Pipeline:
 
     # ------------------------------------------------------------------ loop
     def run_once(self) -> int:
-        """One pass over all stages in topological order; returns the number of records moved."""
-        return (self.stage_documents() + self.stage_sink() + self.stage_queries() + self.stage_search() +
-                self.stage_response())
+        """One pass over all stages in topological order; returns the number of records moved.  The ingest stages
+        are drained completely first, so a query is searched against every document that was already on the
+        log when the pass started (Flink gives no such ordering across topics; this is strictly stronger)."""
+        moved = 0
+        while True:
+            n = self.stage_documents() + self.stage_sink()
+            moved += n
+            if n == 0:
+                break
+        return moved + self.stage_queries() + self.stage_search() + self.stage_response()
 
     def run_until_idle(self, max_passes: int = 1000) -> int:
         total = 0

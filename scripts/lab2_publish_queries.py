@@ -72,7 +72,9 @@ Examples:
   %(prog)s azure --verbose
         """,
     )
-    parser.add_argument("cloud_provider", nargs="?", choices=["aws", "azure"],
+    # The reference declares choices=["aws", "azure"] here, which makes argparse reject its own documented form
+    # `publish_queries "How do window functions work?"` (LAB2-Walkthrough.md:67).  Accept both forms instead.
+    parser.add_argument("cloud_provider", nargs="?", metavar="{aws,azure}",
                         help="Accepted for command-line compatibility; the local engine has no cloud to choose.")
     parser.add_argument("query", nargs="?", help="Query to publish. If not provided, interactive mode will be used.")
     parser.add_argument("--topic", default="queries", help="Topic name (default: queries)")
@@ -81,6 +83,10 @@ Examples:
     args = parser.parse_args(argv)
 
     logger = setup_logging(args.verbose)
+    if args.cloud_provider not in (None, "aws", "azure"):
+        if args.query is not None:
+            parser.error(f"argument cloud_provider: invalid choice: {args.cloud_provider!r} (choose from 'aws', 'azure')")
+        args.query, args.cloud_provider = args.cloud_provider, None   # a lone positional is the query
     if args.cloud_provider:
         logger.debug(f"Ignoring cloud provider argument: {args.cloud_provider}")
 

@@ -1,0 +1,43 @@
+"""Test doubles: an oracle-backed stand-in for engine.VectorIndex so host logic (operator, serve loop, sharding)
+can be exercised on a box without a GPU.  Lives in tests/ -- the product never imports it."""
+import numpy as np
+import torch
+
+from oracle import bruteforce as bf
+
+
+class OracleIndex:
+    def __init__(self, dim, capacity=1 << 20):
+        self.dim = dim
+        self.capacity = capacity
+        self.bits = np.zeros((0, dim), dtype=np.uint16)
+
+    def __len__(self):
+        return len(self.bits)
+
+    def reset(self):
+        self.bits = np.zeros((0, self.dim), dtype=np.uint16)
+
+    def append(self, rows_f32):
+        first = len(self.bits)
+        self.bits = np.concatenate([self.bits, bf.f32_to_bf16_bits(np.asarray(rows_f32, dtype=np.float32))])
+        return first
+
+    def delete_rows(self, rows):
+        self.bits[list(rows)] = 0
+
+    def search_host(self, q_f32, k):
+        s, i = bf.cosine_topk_f64(bf.f32_to_bf16_bits(np.asarray(q_f32, dtype=np.float32)), self.bits, k)
+        return s.astype(np.float32), i.astype(np.int32)
+
+    # torch-tensor flavoured API used by sharded.ShardedIndex
+    def search(self, q, k, want_score64=False):
+        s, i = bf.cosine_topk_f64(bf.f32_to_bf16_bits(q.float().numpy()), self.bits, k)
+        out = (torch.from_numpy(s.astype(np.float32)), torch.from_numpy(i.astype(np.int32)))
+        return out + (torch.from_numpy(s),) if want_score64 else out
+
+    def merge_shards(self, all_s, all_i):
+        g = all_s.shape[0]
+        s, i = bf.merge_shard_topk([all_s[j].numpy() for j in range(g)], [all_i[j].numpy() for j in range(g)],
+                                   [0] * g, all_s.shape[2])
+        return torch.from_numpy(s.astype(np.float32)), torch.from_numpy(i)
