@@ -116,56 +116,57 @@ def run_reference(a):
 # clocks
 # ----------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock, power and throttle reasons of one GPU every ~20 ms on a thread (NVML)."""
 
     def __init__(self, device_index):
         self.idx = device_index
         self.rows = []
-        self.proc = None
+        self._stop = threading.Event()
+        self._t = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.idx]) if vis and vis.split(",")[self.idx].isdigit() else self.idx
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._max = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
         except Exception:
-            self.proc = None
+            return
+        R = pynvml
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), line.strip()))
+        def loop():
+            while not self._stop.is_set():
+                try:
+                    sm = R.nvmlDeviceGetClockInfo(h, R.NVML_CLOCK_SM)
+                    pw = R.nvmlDeviceGetPowerUsage(h) / 1000.0
+                    rs = R.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    self.rows.append((time.perf_counter(), sm, pw, rs))
+                except Exception:
+                    pass
+                time.sleep(0.02)
+
+        self._t = threading.Thread(target=loop, daemon=True)
+        self._t.start()
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=1)
 
     def summary(self, t0, t1):
-        sm, mx, reasons, pw = [], [], set(), []
-        for t, line in self.rows:
-            if t < t0 or t > t1:
-                continue
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 8:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+        import pynvml as R
+        rows = [r for r in self.rows if t0 <= r[0] <= t1]
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
-                "reasons": sorted(reasons), "samples": len(sm)}
+        names = {"hw_slowdown": R.nvmlClocksEventReasonHwSlowdown,
+                 "hw_thermal_slowdown": R.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": R.nvmlClocksEventReasonSwThermalSlowdown,
+                 "sw_power_cap": R.nvmlClocksEventReasonSwPowerCap}
+        reasons = sorted(n for n, bit in names.items() if any(r[3] & bit for r in rows))
+        return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": float(self._max),
+                "power_w_max": float(max(r[2] for r in rows)), "reasons": reasons, "samples": len(rows)}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -188,6 +189,7 @@ def run_b200(a):
     import torch
     import torch.distributed as dist
     from qsa_b200.engine import VectorIndex
+    from qsa_b200.sharded import ShardedIndex
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -215,17 +217,12 @@ def run_b200(a):
     q_host = q_bf16.to(torch.float32).cpu().numpy()  # host fp32 queries (exactly representable in bf16)
     torch.cuda.synchronize()
 
-    gathered_s = torch.empty((world, B, k), dtype=torch.float64, device="cuda") if world > 1 else None
-    gathered_i = torch.empty((world, B, k), dtype=torch.int64, device="cuda") if world > 1 else None
+    sh = ShardedIndex(ix, row_offset=lo_row)
 
     def step_device():
         if world == 1:
             return ix.search(q_bf16, k)
-        s, i, s64 = ix.search(q_bf16, k, want_score64=True)
-        gi = torch.where(i >= 0, i.to(torch.int64) + lo_row, torch.full_like(i, -1, dtype=torch.int64))
-        dist.all_gather_into_tensor(gathered_s, s64)
-        dist.all_gather_into_tensor(gathered_i, gi)
-        return ix.merge_shards(gathered_s, gathered_i)
+        return sh.search(q_bf16, k)          # shard scan -> one all-gather of (cosine, global row) -> merge
 
     def barrier():
         if world > 1:
@@ -239,7 +236,7 @@ def run_b200(a):
 
     sampler = ClockSampler(local)
     sampler.start()
-    time.sleep(0.3)
+    time.sleep(0.1)
 
     # ---- timed: device-resident queries
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -257,7 +254,7 @@ def run_b200(a):
     # per-launch scan time of the LAST step (events live inside the C-ABI, on the launching stream)
     scan_ms_last = t.scan_ms
     launches_per_step = t.launches
-    kernels_per_step = t.kernels + (0 if world == 1 else 1)
+    kernels_per_step = t.kernels + (0 if world == 1 else 1)   # + the shard-merge kernel
 
     # a second short loop that reads the scan events every step (still back to back on the device)
     scan_times = []
@@ -271,15 +268,8 @@ def run_b200(a):
     # ---- timed: e2e with HOST buffers through sa_search_host (+ all-gather/merge for N>1)
     def step_host():
         if world == 1:
-            return ix.search_host(q_host, k)
-        # N>1: host queries -> every rank's shard; results gathered on device, final D2H
-        qd = torch.from_numpy(q_host).cuda(non_blocking=False)
-        s, i, s64 = ix.search(qd, k, want_score64=True)
-        gi = torch.where(i >= 0, i.to(torch.int64) + lo_row, torch.full_like(i, -1, dtype=torch.int64))
-        dist.all_gather_into_tensor(gathered_s, s64)
-        dist.all_gather_into_tensor(gathered_i, gi)
-        fs, fi = ix.merge_shards(gathered_s, gathered_i)
-        return fs.cpu().numpy(), fi.cpu().numpy()
+            return ix.search_host(q_host, k)     # sa_search_host: H2D, convert, scan, merge, D2H
+        return sh.search_host(q_host, k)         # H2D, shard scan, all-gather, merge, D2H
 
     for _ in range(2):
         step_host()
@@ -291,7 +281,7 @@ def run_b200(a):
     e2e_s = time.perf_counter() - t0
     time.sleep(0.2)
     sampler.stop()
-    clocks = sampler.summary(t_w0, t_w1)
+    clocks = sampler.summary(t_w0, time.perf_counter())   # timed loop + scan-event loop + e2e loop, all under load
 
     # max over ranks
     if world > 1:
