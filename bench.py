@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--cta-group", type=int, default=0, help="0 auto, 1, 2")
+    ap.add_argument("--max-drift", type=int, default=-1, help="lockstep drift bound in tiles (-1 = engine default)")
     ap.add_argument("--recall-queries", type=int, default=8, help="queries checked against numpy over ALL rows")
     ap.add_argument("--cpu-sample-queries", type=int, default=256)
     ap.add_argument("--cpu-sample-rows", type=int, default=524_288)
@@ -69,13 +70,15 @@ def measured_peaks():
 # ----------------------------------------------------------------------------------------------------
 # CPU arm (oracle; the only place besides tests/ and smoke() that touches oracle/)
 # ----------------------------------------------------------------------------------------------------
-def cpu_sample_run(q_bits, chunks, k, full_rows):
-    """Time numpy brute force on (queries x sample rows); return (qps scaled to `full_rows`, seconds)."""
+def cpu_sample_run(q_bits, prepared, k, full_rows):
+    """Time numpy brute force on (queries x sample rows) over a corpus already resident in RAM as unit-norm fp32
+    rows (ingest-time work, like the GPU engine's inverse norms, is not timed).  Returns (qps scaled to
+    `full_rows`, seconds)."""
     from oracle import bruteforce as bf
     t0 = time.perf_counter()
-    bf.cosine_topk_sgemm(q_bits, chunks, k)
+    bf.cosine_topk_sgemm_prepared(q_bits, prepared, k)
     dt = time.perf_counter() - t0
-    rows = sum(len(c) for _, c in chunks)
+    rows = sum(len(c) for _, c, _ in prepared)
     qps_full = (len(q_bits) * rows / dt) / full_rows
     return qps_full, dt
 
@@ -92,12 +95,13 @@ def run_reference(a):
         m = min(bf.CHUNK_ROWS, rows - c * bf.CHUNK_ROWS)
         chunks.append((c * bf.CHUNK_ROWS, bf.synth_rows(1234, c, m, a.dim)))
     q = bf.synth_queries(4321, nq, a.dim, chunks[0][1])
+    prepared = bf.prepare_chunks_f32(chunks)
     vals = []
     for _ in range(a.warmup):
-        cpu_sample_run(q[: max(8, nq // 8)], chunks[:1], a.k, a.rows)
+        cpu_sample_run(q[: max(8, nq // 8)], prepared[:1], a.k, a.rows)
     t0 = time.perf_counter()
     for _ in range(a.steps):
-        vals.append(cpu_sample_run(q, chunks, a.k, a.rows)[0])
+        vals.append(cpu_sample_run(q, prepared, a.k, a.rows)[0])
     dt = time.perf_counter() - t0
     v = float(np.median(vals))
     cores = os.cpu_count()
@@ -106,7 +110,7 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic (numpy PCG64, oracle.synth_rows seed 1234/4321)",
-        "config": {"workload": workload_name(a), "k": a.k, "cpu": "numpy fp32 sgemm brute force, all host threads"},
+        "config": {"workload": workload_name(a), "k": a.k, "cpu": "numpy fp32 sgemm brute force over unit-norm fp32 rows in RAM, all BLAS threads"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -209,6 +213,8 @@ def run_b200(a):
     ix = VectorIndex(dim=dim, capacity=n_local, max_batch=B, max_k=k, device=local)
     if a.cta_group:
         ix.set_option("cta_group", a.cta_group)
+    if a.max_drift >= 0:
+        ix.set_option("max_drift", a.max_drift)
     fill_corpus(ix, n_local, dim, seed=1234 + rank)
     g = torch.Generator(device="cuda").manual_seed(4321)
     q_f32 = torch.randn((B, dim), generator=g, device="cuda", dtype=torch.float32)
@@ -251,19 +257,11 @@ def run_b200(a):
     t_w1 = time.perf_counter()
     ms_total = ev0.elapsed_time(ev1)
     t = ix.last_timing()
-    # per-launch scan time of the LAST step (events live inside the C-ABI, on the launching stream)
-    scan_ms_last = t.scan_ms
     launches_per_step = t.launches
     kernels_per_step = t.kernels + (0 if world == 1 else 1)   # + the shard-merge kernel
-
-    # a second short loop that reads the scan events every step (still back to back on the device)
-    scan_times = []
-    barrier()
-    for _ in range(min(a.steps, 5)):
-        step_device()
-        scan_times.append(ix.last_timing().scan_ms)
-    barrier()
-    scan_ms_avg = float(np.mean(scan_times)) if scan_times else scan_ms_last
+    # scan-kernel time: CUDA events recorded inside the C ABI on the launching stream around every scan launch of
+    # the timed loop above (ring of the last 16 searches) -- back to back, no host synchronisation in between
+    scan_ms_avg, _, n_timed = ix.timing_mean(min(a.steps, 16))
 
     # ---- timed: e2e with HOST buffers through sa_search_host (+ all-gather/merge for N>1)
     def step_host():
@@ -310,7 +308,7 @@ def run_b200(a):
             roof = {"bound": "hbm", "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": ach_gbs / peaks["hbm_gbs"], "peak_kind": f"{peaks['source']} copy bandwidth"}
         roof.update({"traffic": None, "kernel": "sa_scan_kernel", "launch_ms": t_launch * 1e3,
-                     "launches_per_step": launches_per_step, "achieved_gbs": ach_gbs, "achieved_tflops": ach_tf,
+                     "launches_per_step": launches_per_step, "launches_timed": n_timed * launches_per_step, "achieved_gbs": ach_gbs, "achieved_tflops": ach_tf,
                      "hbm_frac": ach_gbs / peaks["hbm_gbs"], "tensor_frac_sustained": ach_tf / peaks["tflops_sustained"],
                      "tensor_frac_burst": ach_tf / peaks["tflops_burst"], "scan_share_of_step": scan_ms_avg / (ms_total / a.steps)})
         result = {
@@ -349,12 +347,13 @@ def run_b200(a):
         # CPU baseline on a bounded sample of the same device data
         nsq = min(a.cpu_sample_queries, B)
         qs = q_bf16[:nsq].view(torch.int16).cpu().numpy().view(np.uint16)
-        chunks = list(dev_chunks(a.cpu_sample_rows))
-        cpu_sample_run(qs[:16], chunks[:1], k, n_total)  # warm BLAS threads
-        v, dt = cpu_sample_run(qs, chunks, k, n_total)
+        prepared = bf.prepare_chunks_f32(dev_chunks(a.cpu_sample_rows))
+        cpu_sample_run(qs[:16], prepared[:1], k, n_total)  # warm BLAS threads
+        v, dt = cpu_sample_run(qs, prepared, k, n_total)
         result["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                                  "sample": f"{nsq} queries x {sum(len(c) for _, c in chunks)} rows in {dt:.1f}s "
-                                            f"(numpy fp32 sgemm brute force, QPS scaled to {n_total} rows)"}
+                                  "sample": f"{nsq} queries x {sum(len(c) for _, c, _ in prepared)} rows in {dt:.1f}s "
+                                            f"(numpy fp32 sgemm brute force over unit-norm fp32 rows in RAM, "
+                                            f"QPS scaled to {n_total} rows)"}
     elif rank == 0:
         result.setdefault("cpu_baseline", None)
 

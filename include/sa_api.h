@@ -97,7 +97,12 @@ int sa_merge_shards(sa_engine* e, const double* score64_dev, const int64_t* glob
  * kernels = all kernels the search launched. */
 int sa_last_timing(sa_engine* e, float* scan_ms, float* total_ms, double* bytes, double* flops, int* launches,
                    int* kernels);
-/* Options: "cta_group" = 0 (auto) | 1 | 2;  "max_launch_qblocks" = cap on query blocks per scan launch. */
+/* Mean scan / total milliseconds over the most recent min(n, 16) searches (a ring of CUDA events is kept, so
+ * back-to-back searches can be timed without a host synchronisation between them). */
+int sa_timing_mean(sa_engine* e, int n, float* scan_ms_mean, float* total_ms_mean, int* n_used);
+/* Options: "cta_group" = 0 (auto) | 1 | 2;  "max_launch_qblocks" = cap on query blocks per scan launch;
+ * "max_drift" = tiles a query block may run ahead of the slowest block sharing its corpus tiles (0 = unbounded;
+ * default 2) -- keeps a shared tile L2-resident so it crosses HBM once. */
 int sa_set_option(sa_engine* e, const char* name, int64_t value);
 int sa_get_info(const sa_engine* e, const char* name, int64_t* value); /* "num_sms", "dim", "capacity", "n_rows" */
 

@@ -39,6 +39,8 @@ __all__ = [
     "cosine_topk_f64",
     "cosine_topk_fast",
     "cosine_topk_sgemm",
+    "cosine_topk_sgemm_prepared",
+    "prepare_chunks_f32",
     "compare_topk",
     "merge_shard_topk",
 ]
@@ -168,6 +170,44 @@ def cosine_topk_sgemm(q_bits: np.ndarray, c_chunks, k: int):
         inv = np.where(cn > 0, 1.0 / np.where(cn > 0, cn, 1), 0).astype(np.float32)
         s = (qh @ c.T) * inv[None, :]
         s[:, cn == 0] = -np.inf
+        m = s.shape[1]
+        kk = min(k, m)
+        part = np.argpartition(s, m - kk, axis=1)[:, m - kk :]
+        ps = np.take_along_axis(s, part, axis=1)
+        cs = np.concatenate([best_s, ps], axis=1)
+        ci = np.concatenate([best_i, part.astype(np.int64) + lo], axis=1)
+        order = np.lexsort((ci, -cs), axis=1)[:, :k]
+        best_s = np.take_along_axis(cs, order, axis=1)
+        best_i = np.take_along_axis(ci, order, axis=1)
+    return best_s, best_i
+
+
+def prepare_chunks_f32(c_chunks):
+    """Ingest-time work of a CPU engine, done once and NOT timed by the baseline: upcast each bf16 chunk to fp32
+    and L2-normalise its rows (all-zero rows stay zero and are flagged).  Yields (first_row, unit rows f32, zero mask)."""
+    out = []
+    for lo, bits in c_chunks:
+        c = bf16_bits_to_f32(bits)
+        cn = np.sqrt(np.einsum("ij,ij->i", c, c, dtype=np.float64)).astype(np.float32)
+        zero = cn == 0
+        c /= np.where(zero, 1, cn)[:, None]
+        out.append((lo, c, zero))
+    return out
+
+
+def cosine_topk_sgemm_prepared(q_bits: np.ndarray, prepared, k: int):
+    """The timed CPU baseline: numpy brute force over a corpus that already sits in RAM as unit-norm fp32 rows
+    (``prepare_chunks_f32``).  Per chunk: one sgemm (all BLAS threads) + argpartition top-k + running merge."""
+    q = bf16_bits_to_f32(q_bits)
+    qn = np.sqrt((q.astype(np.float64) ** 2).sum(axis=1)).astype(np.float32)
+    qh = q / np.where(qn > 0, qn, 1)[:, None]
+    nq = q.shape[0]
+    best_s = np.full((nq, k), -np.inf, dtype=np.float32)
+    best_i = np.full((nq, k), -1, dtype=np.int64)
+    for lo, c, zero in prepared:
+        s = qh @ c.T
+        if zero.any():
+            s[:, zero] = -np.inf
         m = s.shape[1]
         kk = min(k, m)
         part = np.argpartition(s, m - kk, axis=1)[:, m - kk :]

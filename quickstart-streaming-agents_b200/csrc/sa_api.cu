@@ -66,6 +66,7 @@ int encode_rows_map(CUtensorMap* m, const void* base, uint64_t rows, int dim, in
 }
 
 constexpr int kMaxLaunches = 16;
+constexpr int kTimingRing = 16;
 
 }  // namespace
 
@@ -98,17 +99,23 @@ struct sa_engine {
   int64_t stage_rows = 0;
   cudaStream_t own_stream = nullptr;
 
+  int* lane_progress = nullptr;  // [num_sms] lockstep counters of the scan (zeroed per launch)
+
   // options
   int opt_cta_group = 0;
   int opt_max_launch_qblocks = 0;
+  int opt_max_drift = 2;
 
-  // timing of the last search
-  cudaEvent_t ev_total[2] = {nullptr, nullptr};
-  cudaEvent_t ev_scan[kMaxLaunches][2];
-  int last_launches = 0;
-  int last_kernels = 0;
-  double last_bytes = 0, last_flops = 0;
-  bool have_timing = false;
+  // timing: CUDA events of the most recent kTimingRing searches
+  struct Timing {
+    cudaEvent_t ev_total[2] = {nullptr, nullptr};
+    cudaEvent_t ev_scan[kMaxLaunches][2];
+    int launches = 0;
+    int kernels = 0;
+    double bytes = 0, flops = 0;
+  };
+  Timing ring[kTimingRing];
+  long long n_searches = 0;
 };
 
 namespace {
@@ -205,6 +212,15 @@ int choose_cg(const sa_engine* e, int nq) {
   return nq > 128 ? 2 : 1;
 }
 
+bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();  // clear the sticky "invalid value" some drivers report for plain malloc memory
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
 int check_engine(const sa_engine* e) {
   if (!e) return fail(SA_ERR_ARG, "null engine");
   if (!e->bound) return fail(SA_ERR_ARG, "no corpus bound (call sa_corpus_bind)");
@@ -227,9 +243,10 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
   if (static_cast<int>(plan.size()) > kMaxLaunches)
     return fail(SA_ERR_CAPACITY, "batch needs %zu scan launches (max %d)", plan.size(), kMaxLaunches);
 
-  e->last_launches = 0;
-  e->last_kernels = 0;
-  SA_CUDA(cudaEventRecord(e->ev_total[0], st));
+  sa_engine::Timing& tm = e->ring[e->n_searches % kTimingRing];
+  tm.launches = 0;
+  tm.kernels = 0;
+  SA_CUDA(cudaEventRecord(tm.ev_total[0], st));
   for (size_t li = 0; li < plan.size(); ++li) {
     const LaunchPlan& lp = plan[li];
     const uint16_t* qptr = q_bf16 + static_cast<size_t>(lp.q0) * e->dim;
@@ -248,14 +265,21 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
     sp.part_score = e->part_score;
     sp.part_idx = e->part_idx;
     sp.corpus_evict_first = (lp.nqb == 1) ? 1 : 0;
+    sp.lane_progress = nullptr;
+    sp.max_drift = 0;
+    if (lp.nqb > 1 && e->opt_max_drift > 0) {
+      sp.lane_progress = e->lane_progress;
+      sp.max_drift = e->opt_max_drift;
+      SA_CUDA(cudaMemsetAsync(e->lane_progress, 0, sizeof(int) * lp.nqb * lp.tl, st));
+    }
     sp.dbg_dots = nullptr;
     sp.dbg_tile = -1;
     const int grid = lp.nqb * lp.tl * lp.cg;
 
-    SA_CUDA(cudaEventRecord(e->ev_scan[li][0], st));
+    SA_CUDA(cudaEventRecord(tm.ev_scan[li][0], st));
     rc = launch_scan_dispatch(lp.cg, kl, false, tq, e->tmap_c[lp.cg - 1], sp, grid, st);
     if (rc) return rc;
-    SA_CUDA(cudaEventRecord(e->ev_scan[li][1], st));
+    SA_CUDA(cudaEventRecord(tm.ev_scan[li][1], st));
 
     sa::MergeParams mp = {};
     mp.part_score = e->part_score;
@@ -276,15 +300,15 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
     else
       sa::sa_merge_rescore_kernel<32><<<lp.nq, sa::kMergeThreads, 0, st>>>(mp);
     SA_CUDA(cudaGetLastError());
-    e->last_launches += 1;
-    e->last_kernels += 2;
+    tm.launches += 1;
+    tm.kernels += 2;
   }
-  SA_CUDA(cudaEventRecord(e->ev_total[1], st));
+  SA_CUDA(cudaEventRecord(tm.ev_total[1], st));
   // Algorithmic work: corpus + inverse norms once per scan launch, queries, results.
   const double n = static_cast<double>(n_rows), d = e->dim, b = nq;
-  e->last_bytes = plan.size() * (n * d * 2.0 + n * 4.0) + b * d * 2.0 + b * k * 8.0;
-  e->last_flops = 2.0 * b * n * d;
-  e->have_timing = true;
+  tm.bytes = plan.size() * (n * d * 2.0 + n * 4.0) + b * d * 2.0 + b * k * 8.0;
+  tm.flops = 2.0 * b * n * d;
+  e->n_searches += 1;
   return SA_OK;
 }
 
@@ -360,12 +384,16 @@ int sa_engine_create(sa_engine** out, int device, int dim, int64_t capacity_rows
   SA_TRY(cudaHostAlloc(&e->h_stage, static_cast<size_t>(e->stage_rows) * dim * 4, cudaHostAllocDefault));
   // a blocking stream: ordered after work already queued on the legacy default stream (torch's default)
   SA_TRY(cudaStreamCreate(&e->own_stream));
-  SA_TRY(cudaEventCreate(&e->ev_total[0]));
-  SA_TRY(cudaEventCreate(&e->ev_total[1]));
-  for (int i = 0; i < kMaxLaunches; ++i) {
-    e->ev_scan[i][0] = e->ev_scan[i][1] = nullptr;
-    SA_TRY(cudaEventCreate(&e->ev_scan[i][0]));
-    SA_TRY(cudaEventCreate(&e->ev_scan[i][1]));
+  SA_TRY(cudaMalloc(&e->lane_progress, sizeof(int) * e->num_sms));
+  for (int r = 0; r < kTimingRing; ++r)
+    for (int i = 0; i < kMaxLaunches; ++i) e->ring[r].ev_scan[i][0] = e->ring[r].ev_scan[i][1] = nullptr;
+  for (int r = 0; r < kTimingRing; ++r) {
+    SA_TRY(cudaEventCreate(&e->ring[r].ev_total[0]));
+    SA_TRY(cudaEventCreate(&e->ring[r].ev_total[1]));
+    for (int i = 0; i < kMaxLaunches; ++i) {
+      SA_TRY(cudaEventCreate(&e->ring[r].ev_scan[i][0]));
+      SA_TRY(cudaEventCreate(&e->ring[r].ev_scan[i][1]));
+    }
   }
 #undef SA_TRY
   *out = e;
@@ -388,11 +416,14 @@ void sa_engine_destroy(sa_engine* e) {
   cudaFreeHost(e->h_idx);
   cudaFreeHost(e->h_stage);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
-  for (int i = 0; i < 2; ++i)
-    if (e->ev_total[i]) cudaEventDestroy(e->ev_total[i]);
-  for (int i = 0; i < kMaxLaunches; ++i)
-    for (int j = 0; j < 2; ++j)
-      if (e->ev_scan[i][j]) cudaEventDestroy(e->ev_scan[i][j]);
+  cudaFree(e->lane_progress);
+  for (int r = 0; r < kTimingRing; ++r) {
+    for (int i = 0; i < 2; ++i)
+      if (e->ring[r].ev_total[i]) cudaEventDestroy(e->ring[r].ev_total[i]);
+    for (int i = 0; i < kMaxLaunches; ++i)
+      for (int j = 0; j < 2; ++j)
+        if (e->ring[r].ev_scan[i][j]) cudaEventDestroy(e->ring[r].ev_scan[i][j]);
+  }
   delete e;
 }
 
@@ -495,7 +526,7 @@ int sa_search_f32(sa_engine* e, const float* q_f32_dev, int nq, int k, float* ou
                                                                                          nullptr, nq, e->dim);
   SA_CUDA(cudaGetLastError());
   rc = do_search(e, e->q_bf16, nq, k, out_score_dev, out_idx_dev, out_score64_dev, st);
-  if (rc == SA_OK) e->last_kernels += 1;
+  if (rc == SA_OK) e->ring[(e->n_searches - 1) % kTimingRing].kernels += 1;
   return rc;
 }
 
@@ -509,15 +540,27 @@ int sa_search_host(sa_engine* e, const float* q_f32_host, int nq, int k, float* 
   SA_CUDA(cudaSetDevice(e->device));
   const size_t qbytes = static_cast<size_t>(nq) * e->dim * 4;
   const size_t rbytes = static_cast<size_t>(nq) * k * 4;
-  memcpy(e->h_q, q_f32_host, qbytes);
-  SA_CUDA(cudaMemcpyAsync(e->q_f32, e->h_q, qbytes, cudaMemcpyHostToDevice, e->own_stream));
+  // Buffers that are already page-locked (sa_host_alloc, cudaHostRegister, torch pin_memory) are DMA'd directly;
+  // pageable ones go through the engine's pinned staging.
+  const bool q_pinned = is_pinned(q_f32_host);
+  const bool r_pinned = is_pinned(out_score_host) && is_pinned(out_idx_host);
+  const float* q_src = q_f32_host;
+  if (!q_pinned) {
+    memcpy(e->h_q, q_f32_host, qbytes);
+    q_src = e->h_q;
+  }
+  SA_CUDA(cudaMemcpyAsync(e->q_f32, q_src, qbytes, cudaMemcpyHostToDevice, e->own_stream));
   rc = sa_search_f32(e, e->q_f32, nq, k, e->res_score, e->res_idx, nullptr, reinterpret_cast<uintptr_t>(e->own_stream));
   if (rc) return rc;
-  SA_CUDA(cudaMemcpyAsync(e->h_score, e->res_score, rbytes, cudaMemcpyDeviceToHost, e->own_stream));
-  SA_CUDA(cudaMemcpyAsync(e->h_idx, e->res_idx, rbytes, cudaMemcpyDeviceToHost, e->own_stream));
+  float* s_dst = r_pinned ? out_score_host : e->h_score;
+  int32_t* i_dst = r_pinned ? out_idx_host : e->h_idx;
+  SA_CUDA(cudaMemcpyAsync(s_dst, e->res_score, rbytes, cudaMemcpyDeviceToHost, e->own_stream));
+  SA_CUDA(cudaMemcpyAsync(i_dst, e->res_idx, rbytes, cudaMemcpyDeviceToHost, e->own_stream));
   SA_CUDA(cudaStreamSynchronize(e->own_stream));
-  memcpy(out_score_host, e->h_score, rbytes);
-  memcpy(out_idx_host, e->h_idx, rbytes);
+  if (!r_pinned) {
+    memcpy(out_score_host, e->h_score, rbytes);
+    memcpy(out_idx_host, e->h_idx, rbytes);
+  }
   return SA_OK;
 }
 
@@ -534,25 +577,62 @@ int sa_merge_shards(sa_engine* e, const double* score64_dev, const int64_t* glob
   return SA_OK;
 }
 
+namespace {
+// Event times of the search `back` positions before the newest one (0 = newest).  Synchronises on its last event.
+int read_timing(sa_engine* e, int back, float* scan_ms, float* total_ms, const sa_engine::Timing** out) {
+  if (e->n_searches <= back || back >= kTimingRing) return fail(SA_ERR_ARG, "no such search in the timing ring");
+  const sa_engine::Timing& tm = e->ring[(e->n_searches - 1 - back) % kTimingRing];
+  SA_CUDA(cudaEventSynchronize(tm.ev_total[1]));
+  float tot = 0.f, scan = 0.f;
+  SA_CUDA(cudaEventElapsedTime(&tot, tm.ev_total[0], tm.ev_total[1]));
+  for (int i = 0; i < tm.launches; ++i) {
+    float ms = 0.f;
+    SA_CUDA(cudaEventElapsedTime(&ms, tm.ev_scan[i][0], tm.ev_scan[i][1]));
+    scan += ms;
+  }
+  *scan_ms = scan;
+  *total_ms = tot;
+  *out = &tm;
+  return SA_OK;
+}
+}  // namespace
+
 int sa_last_timing(sa_engine* e, float* scan_ms, float* total_ms, double* bytes, double* flops, int* launches,
                    int* kernels) {
   if (!e) return fail(SA_ERR_ARG, "null engine");
-  if (!e->have_timing) return fail(SA_ERR_ARG, "no search has run on this engine");
+  if (e->n_searches == 0) return fail(SA_ERR_ARG, "no search has run on this engine");
   SA_CUDA(cudaSetDevice(e->device));
-  SA_CUDA(cudaEventSynchronize(e->ev_total[1]));
-  float tot = 0.f, scan = 0.f;
-  SA_CUDA(cudaEventElapsedTime(&tot, e->ev_total[0], e->ev_total[1]));
-  for (int i = 0; i < e->last_launches; ++i) {
-    float ms = 0.f;
-    SA_CUDA(cudaEventElapsedTime(&ms, e->ev_scan[i][0], e->ev_scan[i][1]));
-    scan += ms;
-  }
+  float scan = 0.f, tot = 0.f;
+  const sa_engine::Timing* tm = nullptr;
+  int rc = read_timing(e, 0, &scan, &tot, &tm);
+  if (rc) return rc;
   if (scan_ms) *scan_ms = scan;
   if (total_ms) *total_ms = tot;
-  if (bytes) *bytes = e->last_bytes;
-  if (flops) *flops = e->last_flops;
-  if (launches) *launches = e->last_launches;
-  if (kernels) *kernels = e->last_kernels;
+  if (bytes) *bytes = tm->bytes;
+  if (flops) *flops = tm->flops;
+  if (launches) *launches = tm->launches;
+  if (kernels) *kernels = tm->kernels;
+  return SA_OK;
+}
+
+int sa_timing_mean(sa_engine* e, int n, float* scan_ms_mean, float* total_ms_mean, int* n_used) {
+  if (!e || !scan_ms_mean || !total_ms_mean || !n_used) return fail(SA_ERR_ARG, "null argument");
+  if (e->n_searches == 0) return fail(SA_ERR_ARG, "no search has run on this engine");
+  SA_CUDA(cudaSetDevice(e->device));
+  const int m = static_cast<int>(std::min<long long>(std::min(n, kTimingRing), e->n_searches));
+  if (m <= 0) return fail(SA_ERR_ARG, "n must be positive");
+  double ssum = 0, tsum = 0;
+  for (int b = 0; b < m; ++b) {
+    float scan = 0.f, tot = 0.f;
+    const sa_engine::Timing* tm = nullptr;
+    int rc = read_timing(e, b, &scan, &tot, &tm);
+    if (rc) return rc;
+    ssum += scan;
+    tsum += tot;
+  }
+  *scan_ms_mean = static_cast<float>(ssum / m);
+  *total_ms_mean = static_cast<float>(tsum / m);
+  *n_used = m;
   return SA_OK;
 }
 
@@ -566,6 +646,11 @@ int sa_set_option(sa_engine* e, const char* name, int64_t value) {
   if (!strcmp(name, "max_launch_qblocks")) {
     if (value < 0) return fail(SA_ERR_ARG, "max_launch_qblocks must be >= 0");
     e->opt_max_launch_qblocks = static_cast<int>(value);
+    return SA_OK;
+  }
+  if (!strcmp(name, "max_drift")) {
+    if (value < 0 || value > 1024) return fail(SA_ERR_ARG, "max_drift must be in [0, 1024]");
+    e->opt_max_drift = static_cast<int>(value);
     return SA_OK;
   }
   return fail(SA_ERR_ARG, "unknown option '%s'", name);
@@ -609,6 +694,8 @@ int sa_debug_tile_dots(sa_engine* e, const void* q_bf16_dev, int nq, int tile, i
   sp.part_score = e->part_score;
   sp.part_idx = e->part_idx;
   sp.corpus_evict_first = 0;
+  sp.lane_progress = nullptr;
+  sp.max_drift = 0;
   sp.dbg_dots = out_dots_dev;
   sp.dbg_tile = tile;
   return launch_scan_dispatch(cta_group, 16, true, tq, e->tmap_c[cta_group - 1], sp, nqb * cta_group,

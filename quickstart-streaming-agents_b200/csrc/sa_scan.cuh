@@ -24,6 +24,7 @@ constexpr int kBlockK = 64;   // bf16 per K slice = 128 B = one swizzle atom
 constexpr int kUmmaK = 16;
 constexpr int kScanThreads = 256;  // w0 TMA, w1 MMA, w2 TMEM alloc, w3 idle, w4..7 epilogue
 constexpr int kTmemCols = 512;
+constexpr int kLockstepMaxSpins = 4096;  // x ~100 ns: give up after ~0.4 ms and run free (hint, not a barrier)
 
 template <int kCG>
 struct ScanCfg {
@@ -49,6 +50,8 @@ struct ScanParams {
   float* part_score;      // [gridDim.x][128][kKL]
   int* part_idx;          // [gridDim.x][128][kKL]
   int corpus_evict_first; // 1: corpus tiles are read by a single query block -> stream them through L2
+  int* lane_progress;     // [tl_count][nqb] tiles whose loads each unit has issued (zeroed before launch), or nullptr
+  int max_drift;          // a unit may run at most this many tiles ahead of its slowest lane-mate (0 = free-running)
   float* dbg_dots;        // debug builds only: raw accumulators of (unit 0 .. nqb-1, tile dbg_tile) [nqb*128*kCG][256]
   int dbg_tile;
 };
@@ -136,7 +139,23 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       const uint64_t c_hint = p.corpus_evict_first ? kEvictFirst : kEvictNormal;
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = tl; t < p.num_tiles; t += TL) {
+      // Bounded-drift lockstep between the query blocks of a tile lane.  Units that share a corpus tile run
+      // identical work but drift apart over thousands of tiles; once the spread exceeds what L2 holds, every
+      // unit re-reads the tile from HBM (measured: 3.05x the algorithmic bytes at B=1024).  Each leader producer
+      // publishes how many tiles it has issued and does not start tile i before all lane-mates issued tile
+      // i - max_drift.  It is a performance hint only: the wait is bounded, so no co-residency assumption and no
+      // deadlock.
+      const bool lockstep = p.lane_progress != nullptr && p.max_drift > 0 && p.nqb > 1 && rank == 0;
+      int it = 0;
+      for (int t = tl; t < p.num_tiles; t += TL, ++it) {
+        if (lockstep && it >= p.max_drift) {
+          const int target = it - p.max_drift + 1;
+          const int* pr = p.lane_progress + tl * p.nqb;
+          int spins = 0;
+          for (int j = 0; j < p.nqb && spins < kLockstepMaxSpins; ++j) {
+            while (ld_acquire_gpu(pr + j) < target && ++spins < kLockstepMaxSpins) __nanosleep(100);
+          }
+        }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           if constexpr (kCG == 1) {
@@ -155,6 +174,7 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             phase ^= 1u;
           }
         }
+        if (lockstep) st_release_gpu(p.lane_progress + tl * p.nqb + qb, it + 1);
       }
     }
   } else if (warp == 1) {

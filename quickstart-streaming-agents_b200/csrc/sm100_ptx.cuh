@@ -89,6 +89,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// gpu-scope flags in global memory
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
 // Cluster
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cluster_sync_all() {

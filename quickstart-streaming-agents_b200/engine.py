@@ -48,6 +48,7 @@ class VectorIndex:
         capi.check(self.lib.sa_engine_create(C.byref(h), self.device, self.dim, self.capacity, self.max_batch,
                                              self.max_k), "sa_engine_create")
         self._h = h
+        self._pinned = []
         capi.check(self.lib.sa_corpus_bind(self._h, self.rows.data_ptr(), self.inv_norm.data_ptr(), 0),
                    "sa_corpus_bind")
 
@@ -56,6 +57,9 @@ class VectorIndex:
         if getattr(self, "_h", None):
             self.lib.sa_engine_destroy(self._h)
             self._h = None
+            for p in self._pinned:
+                self.lib.sa_host_free(p)
+            self._pinned = []
 
     def __del__(self):  # pragma: no cover
         try:
@@ -147,18 +151,33 @@ class VectorIndex:
         capi.check(rc, "sa_search")
         return (score, idx, s64) if want_score64 else (score, idx)
 
-    def search_host(self, q_f32: np.ndarray, k: int):
+    def search_host(self, q_f32: np.ndarray, k: int, out=None):
         """End-to-end path with HOST buffers (H2D, search, D2H inside the call).  Returns numpy
-        (score f32 [nq,k], idx i32 [nq,k])."""
+        (score f32 [nq,k], idx i32 [nq,k]); ``out=(score, idx)`` reuses caller buffers (e.g. ``pinned_array``)."""
         q = np.ascontiguousarray(q_f32, dtype=np.float32)
         assert q.ndim == 2 and q.shape[1] == self.dim
         nq = q.shape[0]
-        score = np.empty((nq, k), dtype=np.float32)
-        idx = np.empty((nq, k), dtype=np.int32)
+        if out is None:
+            score = np.empty((nq, k), dtype=np.float32)
+            idx = np.empty((nq, k), dtype=np.int32)
+        else:
+            score, idx = out
+            assert score.shape == (nq, k) and score.dtype == np.float32 and score.flags.c_contiguous
+            assert idx.shape == (nq, k) and idx.dtype == np.int32 and idx.flags.c_contiguous
         torch.cuda.current_stream(self.device).synchronize()  # the *_host calls run on the engine's stream
         capi.check(self.lib.sa_search_host(self._h, q.ctypes.data, nq, k, score.ctypes.data, idx.ctypes.data),
                    "sa_search_host")
         return score, idx
+
+    def pinned_array(self, shape, dtype=np.float32) -> np.ndarray:
+        """A page-locked numpy array (sa_host_alloc): passing such buffers to ``search_host`` lets the engine DMA
+        them directly instead of staging through its own pinned copy.  Freed when the index is closed."""
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        capi.check(self.lib.sa_host_alloc(C.byref(p), max(nbytes, 1)), "sa_host_alloc")
+        self._pinned.append(p)
+        buf = (C.c_char * nbytes).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
 
     def merge_shards(self, score64_all: torch.Tensor, gidx_all: torch.Tensor):
         """score64_all / gidx_all: [n_shards, nq, k] (float64 / int64 global rows) gathered from all ranks.
@@ -178,6 +197,12 @@ class VectorIndex:
         capi.check(self.lib.sa_last_timing(self._h, C.byref(a), C.byref(b), C.byref(by), C.byref(fl), C.byref(n),
                                            C.byref(kn)), "sa_last_timing")
         return SearchTiming(a.value, b.value, by.value, fl.value, n.value, kn.value)
+
+    def timing_mean(self, n: int = 16) -> tuple[float, float, int]:
+        """(mean scan ms, mean total ms, searches averaged) over the most recent min(n, 16) searches."""
+        a, b, m = C.c_float(), C.c_float(), C.c_int()
+        capi.check(self.lib.sa_timing_mean(self._h, int(n), C.byref(a), C.byref(b), C.byref(m)), "sa_timing_mean")
+        return a.value, b.value, m.value
 
     def debug_tile_dots(self, q_bf16: torch.Tensor, tile: int, cta_group: int = 1) -> torch.Tensor:
         """Test hook: raw Q.C^T accumulators of one 256-row corpus tile, [padded nq, 256] fp32."""
