@@ -99,12 +99,16 @@ struct sa_engine {
   int64_t stage_rows = 0;
   cudaStream_t own_stream = nullptr;
 
+  long long* dbg_times = nullptr;  // [num_sms][2] CTA start/end timestamps of the last scan launch (option "record_times")
+  int opt_record_times = 0;
+  int last_grid = 0;
   int* lane_progress = nullptr;  // [num_sms] lockstep counters of the scan (zeroed per launch)
 
   // options
   int opt_cta_group = 0;
   int opt_max_launch_qblocks = 0;
-  int opt_max_drift = 2;
+  int opt_max_drift = 0;
+  int opt_unit_map = 0;
 
   // timing: CUDA events of the most recent kTimingRing searches
   struct Timing {
@@ -267,6 +271,7 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
     sp.corpus_evict_first = (lp.nqb == 1) ? 1 : 0;
     sp.lane_progress = nullptr;
     sp.max_drift = 0;
+    sp.unit_map = e->opt_unit_map;
     if (lp.nqb > 1 && e->opt_max_drift > 0) {
       sp.lane_progress = e->lane_progress;
       sp.max_drift = e->opt_max_drift;
@@ -274,7 +279,9 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
     }
     sp.dbg_dots = nullptr;
     sp.dbg_tile = -1;
+    sp.dbg_times = e->opt_record_times ? e->dbg_times : nullptr;
     const int grid = lp.nqb * lp.tl * lp.cg;
+    e->last_grid = grid;
 
     SA_CUDA(cudaEventRecord(tm.ev_scan[li][0], st));
     rc = launch_scan_dispatch(lp.cg, kl, false, tq, e->tmap_c[lp.cg - 1], sp, grid, st);
@@ -292,6 +299,7 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
     mp.cg = lp.cg;
     mp.nqb = lp.nqb;
     mp.tl_count = lp.tl;
+    mp.unit_map = e->opt_unit_map;
     mp.out_score = out_score + static_cast<size_t>(lp.q0) * k;
     mp.out_idx = out_idx + static_cast<size_t>(lp.q0) * k;
     mp.out_score64 = out_score64 ? out_score64 + static_cast<size_t>(lp.q0) * k : nullptr;
@@ -385,6 +393,7 @@ int sa_engine_create(sa_engine** out, int device, int dim, int64_t capacity_rows
   // a blocking stream: ordered after work already queued on the legacy default stream (torch's default)
   SA_TRY(cudaStreamCreate(&e->own_stream));
   SA_TRY(cudaMalloc(&e->lane_progress, sizeof(int) * e->num_sms));
+  SA_TRY(cudaMalloc(&e->dbg_times, sizeof(long long) * 2 * e->num_sms));
   for (int r = 0; r < kTimingRing; ++r)
     for (int i = 0; i < kMaxLaunches; ++i) e->ring[r].ev_scan[i][0] = e->ring[r].ev_scan[i][1] = nullptr;
   for (int r = 0; r < kTimingRing; ++r) {
@@ -417,6 +426,7 @@ void sa_engine_destroy(sa_engine* e) {
   cudaFreeHost(e->h_stage);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   cudaFree(e->lane_progress);
+  cudaFree(e->dbg_times);
   for (int r = 0; r < kTimingRing; ++r) {
     for (int i = 0; i < 2; ++i)
       if (e->ring[r].ev_total[i]) cudaEventDestroy(e->ring[r].ev_total[i]);
@@ -648,6 +658,15 @@ int sa_set_option(sa_engine* e, const char* name, int64_t value) {
     e->opt_max_launch_qblocks = static_cast<int>(value);
     return SA_OK;
   }
+  if (!strcmp(name, "record_times")) {
+    e->opt_record_times = value ? 1 : 0;
+    return SA_OK;
+  }
+  if (!strcmp(name, "unit_map")) {
+    if (value < 0 || value > 1) return fail(SA_ERR_ARG, "unit_map must be 0 or 1");
+    e->opt_unit_map = static_cast<int>(value);
+    return SA_OK;
+  }
   if (!strcmp(name, "max_drift")) {
     if (value < 0 || value > 1024) return fail(SA_ERR_ARG, "max_drift must be in [0, 1024]");
     e->opt_max_drift = static_cast<int>(value);
@@ -664,6 +683,8 @@ int sa_get_info(const sa_engine* e, const char* name, int64_t* value) {
   else if (!strcmp(name, "n_rows")) *value = e->n_rows;
   else if (!strcmp(name, "max_batch")) *value = e->max_batch;
   else if (!strcmp(name, "max_k")) *value = e->max_k;
+  else if (!strcmp(name, "last_grid")) *value = e->last_grid;
+  else if (!strcmp(name, "dbg_times_ptr")) *value = static_cast<int64_t>(reinterpret_cast<uintptr_t>(e->dbg_times));
   else return fail(SA_ERR_ARG, "unknown info '%s'", name);
   return SA_OK;
 }
@@ -696,6 +717,8 @@ int sa_debug_tile_dots(sa_engine* e, const void* q_bf16_dev, int nq, int tile, i
   sp.corpus_evict_first = 0;
   sp.lane_progress = nullptr;
   sp.max_drift = 0;
+  sp.unit_map = 0;
+  sp.dbg_times = nullptr;
   sp.dbg_dots = out_dots_dev;
   sp.dbg_tile = tile;
   return launch_scan_dispatch(cta_group, 16, true, tq, e->tmap_c[cta_group - 1], sp, nqb * cta_group,

@@ -94,6 +94,7 @@ struct MergeParams {
   int cg;                   // CTAs per unit in the scan that produced the lists
   int nqb;
   int tl_count;
+  int unit_map;             // same mapping switch as ScanParams::unit_map
   float* out_score;         // [nq][k] fp32 cosine
   int* out_idx;             // [nq][k] shard-local row, -1 when fewer than k rows qualify
   double* out_score64;      // [nq][k] or nullptr: the unrounded cosine, for cross-shard merging
@@ -124,7 +125,8 @@ __global__ void __launch_bounds__(kMergeThreads) sa_merge_rescore_kernel(const M
 
   for (int i = tid; i < ncand; i += kMergeThreads) {
     const int tl = i / kKL, e = i % kKL;
-    const size_t cta = static_cast<size_t>(tl * p.nqb + qb) * p.cg + cta_in_unit;
+    const int unit = p.unit_map == 0 ? tl * p.nqb + qb : qb * p.tl_count + tl;
+    const size_t cta = static_cast<size_t>(unit) * p.cg + cta_in_unit;
     const size_t o = (cta * 128 + row) * kKL + e;
     keys[i] = make_key(p.part_score[o], p.part_idx[o]);
   }

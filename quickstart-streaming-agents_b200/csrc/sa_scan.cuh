@@ -51,7 +51,9 @@ struct ScanParams {
   int* part_idx;          // [gridDim.x][128][kKL]
   int corpus_evict_first; // 1: corpus tiles are read by a single query block -> stream them through L2
   int* lane_progress;     // [tl_count][nqb] tiles whose loads each unit has issued (zeroed before launch), or nullptr
+  int unit_map;           // 0: unit = tl*nqb + qb (lane-mates adjacent), 1: unit = qb*TL + tl (lane-mates TL apart)
   int max_drift;          // a unit may run at most this many tiles ahead of its slowest lane-mate (0 = free-running)
+  long long* dbg_times;   // optional [gridDim.x][2]: globaltimer at CTA start / end (ns), for drift studies
   float* dbg_dots;        // debug builds only: raw accumulators of (unit 0 .. nqb-1, tile dbg_tile) [nqb*128*kCG][256]
   int dbg_tile;
 };
@@ -102,11 +104,12 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   const int lane = threadIdx.x & 31;
   const uint32_t rank = (kCG == 2) ? cluster_ctarank() : 0u;
   const int unit = blockIdx.x / kCG;
-  const int qb = unit % p.nqb;
-  const int tl = unit / p.nqb;
   const int TL = p.tl_count;
+  const int qb = p.unit_map == 0 ? unit % p.nqb : unit / TL;
+  const int tl = p.unit_map == 0 ? unit / p.nqb : unit % TL;
 
   // ------------------------------------------------------------------ one-time setup
+  if (p.dbg_times != nullptr && threadIdx.x == 0) p.dbg_times[2 * blockIdx.x] = globaltimer_ns();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_c);
@@ -308,6 +311,7 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   // ------------------------------------------------------------------ teardown
   tc_fence_before();
   __syncthreads();
+  if (p.dbg_times != nullptr && threadIdx.x == 0) p.dbg_times[2 * blockIdx.x + 1] = globaltimer_ns();
   if constexpr (kCG == 2) cluster_sync_all();  // the peer may still be signalling our barriers / reading our smem
   if (warp == 2) {
     tc_fence_after();

@@ -91,6 +91,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // ----------------------------------------------------------------------------------------------
 // gpu-scope flags in global memory
 // ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long globaltimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
