@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--cta-group", type=int, default=0, help="0 auto, 1, 2")
-    ap.add_argument("--max-drift", type=int, default=-1, help="lockstep drift bound in tiles (-1 = engine default)")
+    ap.add_argument("--pace-gain", type=int, default=-1, help="drift-control gain (-1 = engine default, 0 = off)")
     ap.add_argument("--recall-queries", type=int, default=8, help="queries checked against numpy over ALL rows")
     ap.add_argument("--cpu-sample-queries", type=int, default=256)
     ap.add_argument("--cpu-sample-rows", type=int, default=524_288)
@@ -213,8 +213,8 @@ def run_b200(a):
     ix = VectorIndex(dim=dim, capacity=n_local, max_batch=B, max_k=k, device=local)
     if a.cta_group:
         ix.set_option("cta_group", a.cta_group)
-    if a.max_drift >= 0:
-        ix.set_option("max_drift", a.max_drift)
+    if a.pace_gain >= 0:
+        ix.set_option("pace_gain", a.pace_gain)
     fill_corpus(ix, n_local, dim, seed=1234 + rank)
     g = torch.Generator(device="cuda").manual_seed(4321)
     q_f32 = torch.randn((B, dim), generator=g, device="cuda", dtype=torch.float32)

@@ -101,8 +101,10 @@ int sa_last_timing(sa_engine* e, float* scan_ms, float* total_ms, double* bytes,
  * back-to-back searches can be timed without a host synchronisation between them). */
 int sa_timing_mean(sa_engine* e, int n, float* scan_ms_mean, float* total_ms_mean, int* n_used);
 /* Options: "cta_group" = 0 (auto) | 1 | 2;  "max_launch_qblocks" = cap on query blocks per scan launch;
- * "max_drift" = tiles a query block may run ahead of the slowest block sharing its corpus tiles (0 = unbounded;
- * default 2) -- keeps a shared tile L2-resident so it crosses HBM once. */
+ * drift control between query blocks that share corpus tiles (keeps a shared tile L2-resident so it crosses HBM
+ * once): "max_drift" = unpaced lead in tiles (default 1), "pace_gain" = delay cycles per K-slice per extra tile
+ * of lead (-1 auto, 0 off), "pace_max" = cap of that delay (-1 auto);
+ * "unit_map" = 0 | 1 (CTA -> (query block, tile lane) mapping), "record_times" = 0 | 1 (per-CTA timestamps). */
 int sa_set_option(sa_engine* e, const char* name, int64_t value);
 int sa_get_info(const sa_engine* e, const char* name, int64_t* value); /* "num_sms", "dim", "capacity", "n_rows" */
 

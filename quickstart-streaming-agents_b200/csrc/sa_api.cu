@@ -107,7 +107,9 @@ struct sa_engine {
   // options
   int opt_cta_group = 0;
   int opt_max_launch_qblocks = 0;
-  int opt_max_drift = 0;
+  int opt_max_drift = 1;
+  int opt_pace_gain = -1;  // -1 = auto (16 cycles/tile for CTA pairs, 32 for single CTAs), 0 = off
+  int opt_pace_max = -1;   // -1 = auto (8 x gain)
   int opt_unit_map = 0;
 
   // timing: CUDA events of the most recent kTimingRing searches
@@ -270,11 +272,15 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
     sp.part_idx = e->part_idx;
     sp.corpus_evict_first = (lp.nqb == 1) ? 1 : 0;
     sp.lane_progress = nullptr;
-    sp.max_drift = 0;
+    sp.max_drift = e->opt_max_drift;
+    sp.pace_gain = 0;
+    sp.pace_max = e->opt_pace_max;
     sp.unit_map = e->opt_unit_map;
-    if (lp.nqb > 1 && e->opt_max_drift > 0) {
+    const int gain = e->opt_pace_gain >= 0 ? e->opt_pace_gain : (lp.cg == 2 ? 16 : 32);
+    sp.pace_max = e->opt_pace_max >= 0 ? e->opt_pace_max : 8 * gain;
+    if (lp.nqb > 1 && gain > 0) {
       sp.lane_progress = e->lane_progress;
-      sp.max_drift = e->opt_max_drift;
+      sp.pace_gain = gain;
       SA_CUDA(cudaMemsetAsync(e->lane_progress, 0, sizeof(int) * lp.nqb * lp.tl, st));
     }
     sp.dbg_dots = nullptr;
@@ -667,6 +673,16 @@ int sa_set_option(sa_engine* e, const char* name, int64_t value) {
     e->opt_unit_map = static_cast<int>(value);
     return SA_OK;
   }
+  if (!strcmp(name, "pace_gain")) {
+    if (value < -1 || value > 4096) return fail(SA_ERR_ARG, "pace_gain must be in [-1, 4096]");
+    e->opt_pace_gain = static_cast<int>(value);
+    return SA_OK;
+  }
+  if (!strcmp(name, "pace_max")) {
+    if (value < -1 || value > 65536) return fail(SA_ERR_ARG, "pace_max must be in [-1, 65536]");
+    e->opt_pace_max = static_cast<int>(value);
+    return SA_OK;
+  }
   if (!strcmp(name, "max_drift")) {
     if (value < 0 || value > 1024) return fail(SA_ERR_ARG, "max_drift must be in [0, 1024]");
     e->opt_max_drift = static_cast<int>(value);
@@ -717,6 +733,8 @@ int sa_debug_tile_dots(sa_engine* e, const void* q_bf16_dev, int nq, int tile, i
   sp.corpus_evict_first = 0;
   sp.lane_progress = nullptr;
   sp.max_drift = 0;
+  sp.pace_gain = 0;
+  sp.pace_max = 0;
   sp.unit_map = 0;
   sp.dbg_times = nullptr;
   sp.dbg_dots = out_dots_dev;

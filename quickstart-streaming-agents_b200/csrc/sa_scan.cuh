@@ -24,7 +24,6 @@ constexpr int kBlockK = 64;   // bf16 per K slice = 128 B = one swizzle atom
 constexpr int kUmmaK = 16;
 constexpr int kScanThreads = 256;  // w0 TMA, w1 MMA, w2 TMEM alloc, w3 idle, w4..7 epilogue
 constexpr int kTmemCols = 512;
-constexpr int kLockstepMaxSpins = 4096;  // x ~100 ns: give up after ~0.4 ms and run free (hint, not a barrier)
 
 template <int kCG>
 struct ScanCfg {
@@ -52,7 +51,9 @@ struct ScanParams {
   int corpus_evict_first; // 1: corpus tiles are read by a single query block -> stream them through L2
   int* lane_progress;     // [tl_count][nqb] tiles whose loads each unit has issued (zeroed before launch), or nullptr
   int unit_map;           // 0: unit = tl*nqb + qb (lane-mates adjacent), 1: unit = qb*TL + tl (lane-mates TL apart)
-  int max_drift;          // a unit may run at most this many tiles ahead of its slowest lane-mate (0 = free-running)
+  int max_drift;          // lead (in tiles) over the slowest lane-mate that is not paced
+  int pace_gain;          // SM cycles of delay per K-slice issue per tile of lead beyond max_drift (0 = free-running)
+  int pace_max;           // cap of that delay
   long long* dbg_times;   // optional [gridDim.x][2]: globaltimer at CTA start / end (ns), for drift studies
   float* dbg_dots;        // debug builds only: raw accumulators of (unit 0 .. nqb-1, tile dbg_tile) [nqb*128*kCG][256]
   int dbg_tile;
@@ -142,25 +143,32 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       const uint64_t c_hint = p.corpus_evict_first ? kEvictFirst : kEvictNormal;
       int stage = 0;
       uint32_t phase = 0;
-      // Bounded-drift lockstep between the query blocks of a tile lane.  Units that share a corpus tile run
-      // identical work but drift apart over thousands of tiles; once the spread exceeds what L2 holds, every
-      // unit re-reads the tile from HBM (measured: 3.05x the algorithmic bytes at B=1024).  Each leader producer
-      // publishes how many tiles it has issued and does not start tile i before all lane-mates issued tile
-      // i - max_drift.  It is a performance hint only: the wait is bounded, so no co-residency assumption and no
-      // deadlock.
-      const bool lockstep = p.lane_progress != nullptr && p.max_drift > 0 && p.nqb > 1 && rank == 0;
+      // Drift control between the query blocks of a tile lane.  Units that share a corpus tile run identical work
+      // but at slightly different speeds (measured: ~3 % spread), so over thousands of tiles they drift tens of
+      // tiles apart; once the spread exceeds what L2 holds, every unit re-reads its tiles from HBM (measured
+      // 3.05x the algorithmic bytes at B = 1024).  A hard barrier costs a pipeline drain per tile (measured
+      // +20 %), so the leader producers *pace* themselves instead: each publishes how many tiles it has issued,
+      // reads its lane-mates' counters once per tile, and a unit that leads the slowest mate by more than
+      // `max_drift` tiles delays every K-slice issue by pace_gain cycles per extra tile of lead (capped).  The
+      // kernel's duration is set by its slowest unit anyway, so slowing the fast ones is free; it is only a
+      // hint (no waiting on anyone), hence no co-residency assumption and no deadlock.
+      const bool lockstep = p.lane_progress != nullptr && p.pace_gain > 0 && p.nqb > 1 && rank == 0;
+      int pace = 0;
       int it = 0;
       for (int t = tl; t < p.num_tiles; t += TL, ++it) {
-        if (lockstep && it >= p.max_drift) {
-          const int target = it - p.max_drift + 1;
+        if (lockstep) {
           const int* pr = p.lane_progress + tl * p.nqb;
-          int spins = 0;
-          for (int j = 0; j < p.nqb && spins < kLockstepMaxSpins; ++j) {
-            while (ld_acquire_gpu(pr + j) < target && ++spins < kLockstepMaxSpins) __nanosleep(100);
-          }
+          int slowest = it;
+          for (int j = 0; j < p.nqb; ++j) slowest = min(slowest, ld_relaxed_gpu(pr + j));
+          pace = min(max(it - slowest - p.max_drift, 0) * p.pace_gain, p.pace_max);
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (pace > 0) {
+            const long long c0 = clock64();
+            while (clock64() - c0 < pace) {
+            }
+          }
           if constexpr (kCG == 1) {
             mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
             tma_load_2d(a_smem(stage), &tmap_q, full_bar(stage), kb * kBlockK, qb * kBlockM, kEvictLast);
@@ -177,7 +185,7 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             phase ^= 1u;
           }
         }
-        if (lockstep) st_release_gpu(p.lane_progress + tl * p.nqb + qb, it + 1);
+        if (lockstep) st_relaxed_gpu(p.lane_progress + tl * p.nqb + qb, it + 1);
       }
     }
   } else if (warp == 1) {

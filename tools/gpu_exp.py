@@ -39,20 +39,14 @@ def run(ix, q, k, iters, label, host_q=None, pinned=None):
 if __name__ == "__main__":
     rows = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
     dim = int(sys.argv[2]) if len(sys.argv) > 2 else 1536
+    B = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
+    # settings: "cg,drift,gain,max;..."
+    settings = [tuple(int(x) for x in s.split(",")) for s in (sys.argv[4] if len(sys.argv) > 4 else "2,1,0,128").split(";")]
+    iters = int(sys.argv[5]) if len(sys.argv) > 5 else 10
     ix = VectorIndex(dim=dim, capacity=rows, max_batch=4096, max_k=10)
     fill_corpus(ix, rows, dim, 1234)
     g = torch.Generator(device="cuda").manual_seed(1)
-    for B in (1024, 4096, 256, 128):
-        q = torch.randn((B, dim), generator=g, device="cuda").to(torch.bfloat16)
-        hq = q.float().cpu().numpy()
-        pq = ix.pinned_array((B, dim), np.float32); pq[:] = hq
-        ps = ix.pinned_array((B, 10), np.float32); pi = ix.pinned_array((B, 10), np.int32)
-        if B > 128:
-            for cg in (2, 1):
-                ix.set_option("cta_group", cg)
-                for d in ((0, 1, 2, 3, 4, 8) if B == 1024 else (0, 2)):
-                    ix.set_option("max_drift", d)
-                    run(ix, q, 10, 10, f"B={B} cg={cg} drift={d}", hq if (d == 2 and cg == 2) else None, (pq, ps, pi))
-        else:
-            ix.set_option("cta_group", 0)
-            run(ix, q, 10, 10, f"B={B} auto", hq, (pq, ps, pi))
+    q = torch.randn((B, dim), generator=g, device="cuda").to(torch.bfloat16)
+    for cg, d, gain, mx in settings:
+        ix.set_option("cta_group", cg); ix.set_option("max_drift", d); ix.set_option("pace_gain", gain); ix.set_option("pace_max", mx)
+        run(ix, q, 10, iters, f"B={B} cg={cg} drift={d} gain={gain} max={mx}")
