@@ -220,7 +220,11 @@ def run_b200(a):
     q_f32 = torch.randn((B, dim), generator=g, device="cuda", dtype=torch.float32)
     # plant half of the queries next to rows of rank 0's shard start (known neighbours exist)
     q_bf16 = q_f32.to(torch.bfloat16)
-    q_host = q_bf16.to(torch.float32).cpu().numpy()  # host fp32 queries (exactly representable in bf16)
+    # host fp32 queries (exactly representable in bf16) and host result buffers, page-locked through the C ABI
+    # (sa_host_alloc) as a serving loop would hold them, so sa_search_host DMAs them without a staging copy
+    q_host = ix.pinned_array((B, dim), np.float32)
+    q_host[:] = q_bf16.to(torch.float32).cpu().numpy()
+    out_host = (ix.pinned_array((B, k), np.float32), ix.pinned_array((B, k), np.int32))
     torch.cuda.synchronize()
 
     sh = ShardedIndex(ix, row_offset=lo_row)
@@ -266,7 +270,7 @@ def run_b200(a):
     # ---- timed: e2e with HOST buffers through sa_search_host (+ all-gather/merge for N>1)
     def step_host():
         if world == 1:
-            return ix.search_host(q_host, k)     # sa_search_host: H2D, convert, scan, merge, D2H
+            return ix.search_host(q_host, k, out=out_host)     # sa_search_host: H2D, convert, scan, merge, D2H
         return sh.search_host(q_host, k)         # H2D, shard scan, all-gather, merge, D2H
 
     for _ in range(2):
@@ -319,7 +323,9 @@ def run_b200(a):
                        "parallelism": f"row-shard x{world}" if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (corpus shard %.1f GB per step)" % (n_local * dim * 2 / 1e9),
                        "cta_group": a.cta_group or "auto"},
-            "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": B * dim * 4, "d2h_bytes_per_step": B * k * (8 if world == 1 else 12)},
+            "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": B * dim * 4, "d2h_bytes_per_step": B * k * (8 if world == 1 else 12),
+                    "api": "sa_search_host (C ABI, host fp32 queries in, host results out, page-locked buffers)" if world == 1 else
+                           "ShardedIndex.search_host (H2D, shard scan, NCCL all-gather, merge, D2H)"},
             "gpu_launches": int(kernels_per_step * a.steps),
             "clocks": clocks, "roofline": roof,
         }
@@ -354,6 +360,41 @@ def run_b200(a):
                                   "sample": f"{nsq} queries x {sum(len(c) for _, c, _ in prepared)} rows in {dt:.1f}s "
                                             f"(numpy fp32 sgemm brute force over unit-norm fp32 rows in RAM, "
                                             f"QPS scaled to {n_total} rows)"}
+    elif world > 1 and not a.no_cpu:
+        # N>1 parity (outside the timed region): every rank runs the oracle over ITS shard for a few queries, the
+        # per-shard oracle lists are gathered and merged on the CPU, and rank 0 compares that with what the engine's
+        # shard scan + all-gather + merge kernel returned.  Also checks that every rank ended with the same answer.
+        from oracle import bruteforce as bf
+        got_s, got_i = [x.cpu().numpy() for x in out]
+        nrq = min(max(2, a.recall_queries // 2), B)
+        qb = q_bf16[:nrq].view(torch.int16).cpu().numpy().view(np.uint16)
+
+        def dev_chunks():
+            step = 1 << 18
+            for lo in range(0, n_local, step):
+                m = min(step, n_local - lo)
+                yield lo, ix.rows[lo:lo + m].view(torch.int16).cpu().numpy().view(np.uint16)
+
+        rs, ri = bf.cosine_topk_fast(qb, dev_chunks(), k)
+        ts = torch.from_numpy(rs).cuda()
+        ti = torch.from_numpy(np.where(ri >= 0, ri + lo_row, -1)).cuda()
+        all_s = [torch.empty_like(ts) for _ in range(world)]
+        all_i = [torch.empty_like(ti) for _ in range(world)]
+        dist.all_gather(all_s, ts)
+        dist.all_gather(all_i, ti)
+        mine = torch.from_numpy(got_i).cuda()
+        ref0 = mine.clone()
+        dist.broadcast(ref0, src=0)
+        same = torch.tensor([int(torch.equal(mine, ref0))], device="cuda")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            ms, mi = bf.merge_shard_topk([x.cpu().numpy() for x in all_s], [x.cpu().numpy() for x in all_i],
+                                         [0] * world, k)
+            rep = bf.compare_topk(got_i[:nrq], got_s[:nrq], mi, ms)
+            result["recall"] = {"queries_checked": nrq, "rows": n_total, "recall_at_k": rep["recall"],
+                                "strict_order": rep["strict_order"], "max_abs_dscore": rep["max_abs_dscore"],
+                                "all_ranks_same_answer": bool(same.item())}
+            result["cpu_baseline"] = None
     elif rank == 0:
         result.setdefault("cpu_baseline", None)
 

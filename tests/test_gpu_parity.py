@@ -219,3 +219,20 @@ def test_full_size_properties_1M(bf):
     assert (gi[sample] == ri).all()
     assert np.abs(gs[sample].astype(np.float64) - rs).max() < SCORE_TOL
     ix.close()
+
+
+def test_drift_control_and_mapping_options_do_not_change_answers(bf):
+    """Pacing, unit mapping and CTA grouping only move work around in time and space."""
+    from qsa_b200.engine import VectorIndex
+    dim, n, nq, k = 128, 60000, 700, 10
+    c = bf.synth_rows(51, 0, n, dim)
+    q = bf.synth_queries(52, nq, dim, c)
+    ix = VectorIndex(dim=dim, capacity=n, max_batch=1024, max_k=10)
+    ix.append_bf16_bits(c)
+    for cg in (1, 2):
+        for gain, drift, umap in ((0, 1, 0), (16, 1, 0), (64, 0, 1), (4096, 0, 0)):
+            ix.set_option("pace_gain", gain); ix.set_option("max_drift", drift); ix.set_option("unit_map", umap)
+            check(ix, q, c, k, cg)
+    scan, total, m = ix.timing_mean(16)
+    assert m == 8 and 0 < scan <= total
+    ix.close()
