@@ -108,6 +108,24 @@ def flatten_search_results(query: str | None, hits: list[SearchHit], n: int = 3)
     return rec
 
 
+def project_search_results(hits: list[SearchHit], columns: dict[str, str], n: int = 3) -> dict:
+    """Generic form of the projection for tables with metadata columns, e.g. Lab4's
+    ``vs.search_results[i].chunk AS policy_chunk_i, ... .pages AS policy_pages_i, ...`` (LAB4-Walkthrough.md:280-300):
+    ``columns`` maps a table column (document_id, chunk, score or a metadata column) to its output prefix."""
+    rec = {}
+    for i in range(1, n + 1):
+        h = hits[i - 1] if i <= len(hits) else None
+        for col, prefix in columns.items():
+            if h is None:
+                v = None
+            elif col in ("document_id", "chunk", "score"):
+                v = getattr(h, col)
+            else:
+                v = h.metadata.get(col)
+            rec[f"{prefix}_{i}"] = v
+    return rec
+
+
 def rag_prompt(rec: dict) -> str:
     """The CONCAT(...) of main.tf:331, character for character (SQL '' -> ', \\n -> newline)."""
     def s(v):

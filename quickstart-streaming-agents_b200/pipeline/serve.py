@@ -116,8 +116,9 @@ class Lab2Pipeline:
         for m, r in recs:
             text = r.get("document_text") or ""
             vec = self.embedder.embed(text)
-            self.producer.produce("documents_embed", key=m.key(), value=self.codec.encode(
-                "documents_embed", {"document_id": r.get("document_id"), "chunk": text, "embedding": vec}))
+            out = {"document_id": r.get("document_id"), "chunk": text, "embedding": vec}
+            out.update({c: r.get(c) for c in schemas.METADATA_COLUMNS})   # Lab4-style metadata passthrough
+            self.producer.produce("documents_embed", key=m.key(), value=self.codec.encode("documents_embed", out))
         if msgs:
             self.producer.flush()
             c.commit()
@@ -125,7 +126,7 @@ class Lab2Pipeline:
 
     def stage_sink(self) -> int:
         c, msgs, recs = self._drain("documents_embed")
-        ids, chunks, vecs = [], [], []
+        ids, chunks, vecs, metas = [], [], [], []
         for m, r in recs:
             vec = r.get("embedding")
             if not self._check_vec("documents_embed", m, vec):
@@ -133,8 +134,9 @@ class Lab2Pipeline:
             ids.append(r.get("document_id"))
             chunks.append(r.get("chunk"))
             vecs.append(vec)
+            metas.append({c: r.get(c) for c in schemas.METADATA_COLUMNS})
         if ids:
-            self.table.upsert_many(ids, chunks, np.stack(vecs))
+            self.table.upsert_many(ids, chunks, np.stack(vecs), metas)
             self.stats["documents"] += len(ids)
         if msgs:
             self.producer.flush()

@@ -58,11 +58,19 @@ QUERIES_EMBED_VALUE = {
     "fields": [_field("query", "string"), _field("embedding", _FLOAT_ARRAY)],
 }
 
+# Columns of the vector tables: Lab2/Lab3 use (document_id, chunk, embedding) (main.tf:215;
+# terraform/lab3-agentic-fleet-management/main.tf:110-124); Lab4's fema_policies_vectordb adds the metadata columns
+# of the documents topic (terraform/lab4-pubsec-fraud-agents/main.tf:271-289).  One schema carries them all.
+METADATA_COLUMNS = ("pages", "section_reference", "title", "fraud_categories", "policy_keywords", "char_count")
+
 DOCUMENTS_EMBED_VALUE = {
     "type": "record",
     "name": "documents_embed_value",
     "namespace": NAMESPACE,
-    "fields": [_field("document_id", "string"), _field("chunk", "string"), _field("embedding", _FLOAT_ARRAY)],
+    "fields": [_field("document_id", "string"), _field("chunk", "string"), _field("embedding", _FLOAT_ARRAY),
+               _field("pages", "string"), _field("section_reference", "string"), _field("title", "string"),
+               _field("fraud_categories", _STRING_ARRAY), _field("policy_keywords", _STRING_ARRAY),
+               _field("char_count", "int")],
 }
 
 RESULTS_PER_QUERY = 3  # the reference flattens search_results[1..3] (main.tf:292)

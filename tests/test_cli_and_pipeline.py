@@ -192,6 +192,31 @@ def test_flatten_and_prompt_follow_the_sql():
     assert avro.decode(schemas.SEARCH_RESULTS_VALUE, body) == rec
 
 
+def test_lab3_and_lab4_operator_shapes(tmp_path):
+    """The other two call sites of the operator: Lab3 (top-3 chunks of an events collection, LAB3-Walkthrough.md:343-350)
+    and Lab4 (metadata columns projected next to chunk/score, LAB4-Walkthrough.md:280-309)."""
+    from qsa_b200.operator import project_search_results
+    docs, logd = tmp_path / "docs", str(tmp_path / "topics")
+    write_docs(docs, 24)
+    assert publish_docs.main(["--docs-dir", str(docs), "--log-dir", logd]) == 0
+    table = VectorTable(OracleIndex(768), name="fema_policies_vectordb")        # 768-d: dim is a runtime parameter
+    emb = StubEmbedder(768)
+    pipe = Lab2Pipeline(logd, table, embedder=emb, k=5)
+    pipe.run_until_idle()
+    hits = vector_search_agg(table, "embedding", emb.embed("late data and watermarks in event time"), 5)[0]
+    assert len(hits) == 5 and "watermarks" in hits[0].chunk.lower()
+    rec = project_search_results(hits, {"chunk": "policy_chunk", "score": "policy_score", "pages": "policy_pages",
+                                        "section_reference": "policy_section", "title": "policy_title",
+                                        "fraud_categories": "policy_fraud_cats", "policy_keywords": "policy_keywords"}, 3)
+    assert set(rec) == {f"{p}_{i}" for i in (1, 2, 3) for p in ("policy_chunk", "policy_score", "policy_pages",
+                        "policy_section", "policy_title", "policy_fraud_cats", "policy_keywords")}
+    assert rec["policy_title_1"].startswith("Watermarks And Event Time") and rec["policy_keywords_1"] == ["watermarks", "sql"]
+    assert rec["policy_pages_1"] is not None and rec["policy_section_1"].startswith("S") and rec["policy_fraud_cats_1"] is None
+    assert rec["policy_score_1"] >= rec["policy_score_2"] >= rec["policy_score_3"]
+    lab3 = project_search_results(hits, {"chunk": "top_chunk"}, 3)                 # testing/e2e/test_lab3.py:232-268
+    assert lab3["top_chunk_1"] and lab3["top_chunk_2"]
+
+
 @pytest.mark.gpu
 def test_pipeline_on_gpu(tmp_path):
     from qsa_b200.engine import VectorIndex
