@@ -311,7 +311,17 @@ def run_b200(a):
         else:
             roof = {"bound": "hbm", "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": ach_gbs / peaks["hbm_gbs"], "peak_kind": f"{peaks['source']} copy bandwidth"}
-        roof.update({"traffic": None, "kernel": "sa_scan_kernel", "launch_ms": t_launch * 1e3,
+        traffic = None
+        try:   # dram__bytes_read + write of this kernel from the committed `ncu --set full` capture of this workload
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                tj = json.load(f).get(f"{n_local}x{dim}_b{B}_k{k}")
+            if tj and world == 1:
+                traffic = tj["dram_bytes_per_launch"]
+                roof["traffic_source"] = tj["source"]
+                roof["algorithmic_bytes"] = bytes_launch
+        except Exception:
+            pass
+        roof.update({"traffic": traffic, "kernel": "sa_scan_kernel", "launch_ms": t_launch * 1e3,
                      "launches_per_step": launches_per_step, "launches_timed": n_timed * launches_per_step, "achieved_gbs": ach_gbs, "achieved_tflops": ach_tf,
                      "hbm_frac": ach_gbs / peaks["hbm_gbs"], "tensor_frac_sustained": ach_tf / peaks["tflops_sustained"],
                      "tensor_frac_burst": ach_tf / peaks["tflops_burst"], "scan_share_of_step": scan_ms_avg / (ms_total / a.steps)})
