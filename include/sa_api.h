@@ -113,6 +113,11 @@ int sa_get_info(const sa_engine* e, const char* name, int64_t* value); /* "num_s
 int sa_debug_tile_dots(sa_engine* e, const void* q_bf16_dev, int nq, int tile, int cta_group, float* out_dots_dev,
                        uintptr_t stream);
 
+/* Test hook (pure host logic, no GPU needed): how a batch of nq queries is split into scan launches on a device
+ * with num_sms SMs.  out receives up to max_out rows of {first query, queries, query blocks, tile lanes}. */
+int sa_debug_plan(int num_sms, int nq, int cta_group, int num_tiles, int max_launch_qblocks, int* out, int max_out,
+                  int* n_launches);
+
 /* Pinned host memory for callers that want truly asynchronous staging. */
 int sa_host_alloc(void** out, uint64_t bytes);
 int sa_host_free(void* p);

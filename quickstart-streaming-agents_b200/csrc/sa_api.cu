@@ -137,12 +137,12 @@ struct LaunchPlan {
 // Split the batch into scan launches.  A launch with nqb query blocks runs TL = floor(units / nqb) tile
 // lanes, each walking ceil(num_tiles / TL) tiles; pick the split that minimises the summed tile walks
 // (fewer launches win ties: every launch re-streams the corpus through HBM once).
-std::vector<LaunchPlan> plan_search(const sa_engine* e, int nq, int cg, int num_tiles) {
+std::vector<LaunchPlan> plan_search(int num_sms, int max_launch_qblocks, int nq, int cg, int num_tiles) {
   const int rows_per_qb = 128 * cg;
-  const int units = e->num_sms / cg;
+  const int units = num_sms / cg;
   const int nqb_total = (nq + rows_per_qb - 1) / rows_per_qb;
   int cap = units;
-  if (e->opt_max_launch_qblocks > 0) cap = std::min(cap, e->opt_max_launch_qblocks);
+  if (max_launch_qblocks > 0) cap = std::min(cap, max_launch_qblocks);
   long best_cost = -1;
   int best_l = 1;
   const int l_min = (nqb_total + cap - 1) / cap;
@@ -245,7 +245,7 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
   const int64_t n_rows = e->n_rows;
   const int num_tiles = static_cast<int>((n_rows + sa::kBlockN - 1) / sa::kBlockN);
   const int cg = choose_cg(e, nq);
-  std::vector<LaunchPlan> plan = plan_search(e, nq, cg, std::max(num_tiles, 1));
+  std::vector<LaunchPlan> plan = plan_search(e->num_sms, e->opt_max_launch_qblocks, nq, cg, std::max(num_tiles, 1));
   if (static_cast<int>(plan.size()) > kMaxLaunches)
     return fail(SA_ERR_CAPACITY, "batch needs %zu scan launches (max %d)", plan.size(), kMaxLaunches);
 
@@ -741,6 +741,23 @@ int sa_debug_tile_dots(sa_engine* e, const void* q_bf16_dev, int nq, int tile, i
   sp.dbg_tile = tile;
   return launch_scan_dispatch(cta_group, 16, true, tq, e->tmap_c[cta_group - 1], sp, nqb * cta_group,
                               reinterpret_cast<cudaStream_t>(stream));
+}
+
+int sa_debug_plan(int num_sms, int nq, int cta_group, int num_tiles, int max_launch_qblocks, int* out, int max_out,
+                  int* n_launches) {
+  if (!out || !n_launches) return fail(SA_ERR_ARG, "null argument");
+  if (num_sms < 2 || nq <= 0 || num_tiles < 0 || (cta_group != 1 && cta_group != 2))
+    return fail(SA_ERR_ARG, "bad planning input");
+  std::vector<LaunchPlan> plan = plan_search(num_sms, max_launch_qblocks, nq, cta_group, std::max(num_tiles, 1));
+  if (static_cast<int>(plan.size()) > max_out) return fail(SA_ERR_CAPACITY, "plan has %zu launches", plan.size());
+  for (size_t i = 0; i < plan.size(); ++i) {
+    out[4 * i + 0] = plan[i].q0;
+    out[4 * i + 1] = plan[i].nq;
+    out[4 * i + 2] = plan[i].nqb;
+    out[4 * i + 3] = plan[i].tl;
+  }
+  *n_launches = static_cast<int>(plan.size());
+  return SA_OK;
 }
 
 int sa_host_alloc(void** out, uint64_t bytes) {

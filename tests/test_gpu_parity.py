@@ -236,3 +236,61 @@ def test_drift_control_and_mapping_options_do_not_change_answers(bf):
     scan, total, m = ix.timing_mean(16)
     assert m == 8 and 0 < scan <= total
     ix.close()
+
+
+def test_full_size_properties_10M(bf):
+    """BASELINE.json's full size (10M x 1536 bf16, batch 1024, top-10) through size-independent properties:
+    planted queries return their planted row first; scores are sorted and equal an independent float64 cosine of the
+    returned rows; searching two row shards and merging equals searching the whole; batch position does not matter."""
+    import torch
+    from qsa_b200.engine import VectorIndex
+    free, _ = torch.cuda.mem_get_info()
+    if free < 70e9:
+        pytest.skip("needs ~65 GB of free HBM")
+    dim, n, nq, k = 1536, 10_000_000, 1024, 10
+    ix = VectorIndex(dim=dim, capacity=n, max_batch=nq, max_k=k)
+    g = torch.Generator(device="cuda").manual_seed(99)
+    step = 1 << 18
+    for lo in range(0, n, step):
+        m = min(step, n - lo)
+        x = torch.randn((m, dim), generator=g, device="cuda")
+        x *= torch.exp(torch.empty((m, 1), device="cuda").uniform_(-0.7, 0.7, generator=g))
+        ix.rows[lo:lo + m].copy_(x)
+    ix.commit(0, n)
+    planted = (torch.arange(nq, device="cuda", dtype=torch.int64) * 2654435761) % n
+    q = torch.randn((nq, dim), generator=g, device="cuda")
+    base = ix.rows[planted[1::2]].float()
+    q[1::2] = base + 0.5 * base.norm(dim=1, keepdim=True) / dim ** 0.5 * torch.randn(base.shape, generator=g, device="cuda")
+    q = q.to(torch.bfloat16)
+    s, i, s64 = ix.search(q, k, want_score64=True)
+    torch.cuda.synchronize()
+    gi = i.cpu().numpy().astype(np.int64)
+    assert (gi[1::2, 0] == planted[1::2].cpu().numpy()).all()                        # known neighbours come first
+    s64c = s64.cpu().numpy()
+    assert (np.diff(s64c, axis=1) <= 0).all() and (gi >= 0).all()
+    assert all(len(set(r)) == k for r in gi.tolist())
+    # returned scores == independent float64 cosine of the returned rows (a sample of queries, CPU arithmetic)
+    for r in range(0, nq, 37):
+        rows = bf.bf16_bits_to_f32(ix.rows[i[r].long()].view(torch.int16).cpu().numpy().view(np.uint16)).astype(np.float64)
+        qq = bf.bf16_bits_to_f32(q[r:r + 1].view(torch.int16).cpu().numpy().view(np.uint16)).astype(np.float64)[0]
+        cos = rows @ qq / np.sqrt((rows * rows).sum(1) * (qq * qq).sum())
+        assert np.abs(cos - s64c[r]).max() < 1e-12 and np.abs(cos - s.cpu().numpy()[r]).max() < SCORE_TOL
+    # a permutation of the batch permutes the answers (no cross-query leakage, launch split independent)
+    perm = torch.randperm(nq, generator=torch.Generator().manual_seed(5))
+    s2, i2 = ix.search(q[perm.cuda()], k)
+    assert torch.equal(i2.cpu(), i.cpu()[perm])
+    # shard-and-merge == whole (two row shards re-indexed on the same GPU)
+    cut = 4_500_000
+    parts = []
+    for lo, hi in ((0, cut), (cut, n)):
+        sub = VectorIndex(dim=dim, capacity=hi - lo, max_batch=256, max_k=k)
+        sub.rows.copy_(ix.rows[lo:hi])
+        sub.commit(0, hi - lo)
+        ss, si, ss64 = sub.search(q[:256], k, want_score64=True)
+        parts.append((ss64, torch.where(si >= 0, si.to(torch.int64) + lo, torch.full_like(si, -1, dtype=torch.int64)), sub))
+    fs, fi = ix.merge_shards(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
+    torch.cuda.synchronize()
+    assert torch.equal(fi.cpu(), i[:256].cpu().to(torch.int64))
+    for p in parts:
+        p[2].close()
+    ix.close()
