@@ -16,6 +16,7 @@ with the error text in its key, and the stage moves on.
 from __future__ import annotations
 
 import logging
+import struct
 import time
 
 import numpy as np
@@ -44,23 +45,37 @@ def stub_generator(prompt: str, rec: dict) -> str:
 
 
 class Codec:
-    """Avro + Confluent framing for one log directory (schema ids from the registry stub)."""
+    """Avro + Confluent framing for one log directory (schema ids from the registry stub, compiled codecs)."""
 
     def __init__(self, log_dir: str):
         self.registry = SchemaRegistry(log_dir)
-        self._ids: dict[str, int] = {}
+        self._enc: dict[str, tuple[bytes, avro.CompiledSchema]] = {}
+        self._dec: dict[int, avro.CompiledSchema] = {}
 
     def schema_id(self, topic: str) -> int:
-        if topic not in self._ids:
-            self._ids[topic] = self.registry.register(f"{topic}-value", schemas.TOPIC_SCHEMAS[topic])
-        return self._ids[topic]
+        return struct.unpack(">I", self._encoder(topic)[0][1:5])[0]
+
+    def _encoder(self, topic: str):
+        e = self._enc.get(topic)
+        if e is None:
+            sid = self.registry.register(f"{topic}-value", schemas.TOPIC_SCHEMAS[topic])
+            e = self._enc[topic] = (avro.frame(sid, b""), avro.CompiledSchema(schemas.TOPIC_SCHEMAS[topic]))
+        return e
 
     def encode(self, topic: str, record: dict) -> bytes:
-        return avro.frame(self.schema_id(topic), avro.encode(schemas.TOPIC_SCHEMAS[topic], record))
+        header, cs = self._encoder(topic)
+        return cs.encode(record, prefix=header)
 
     def decode(self, raw: bytes) -> dict:
-        sid, body = avro.unframe(raw)
-        return avro.decode(self.registry.get(sid), body)
+        if len(raw) < 5:
+            raise avro.AvroError(f"Avro payload too short ({len(raw)} bytes)")
+        if raw[0] != avro.MAGIC:
+            raise avro.AvroError(f"Invalid Avro magic byte: {raw[0]}")
+        sid = struct.unpack_from(">I", raw, 1)[0]
+        cs = self._dec.get(sid)
+        if cs is None:
+            cs = self._dec[sid] = avro.CompiledSchema(self.registry.get(sid))
+        return cs.decode(raw, 5)
 
 
 class Lab2Pipeline:

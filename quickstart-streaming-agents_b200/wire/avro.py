@@ -407,3 +407,212 @@ def from_avro_json(schema: Any, j: Any) -> Any:
     if schema in ("int", "long"):
         return int(j)
     return j
+
+
+# ----------------------------------------------------------------------------------------------------
+# compiled codecs: one closure tree per schema, built once -- the serve loop's per-record hot path.
+# (The generic encode()/decode() above are the readable statement of the rules; tests pin these against them.)
+# ----------------------------------------------------------------------------------------------------
+_pack_f = struct.Struct("<f").pack
+_pack_d = struct.Struct("<d").pack
+_unpack_f = struct.Struct("<f").unpack_from
+_unpack_d = struct.Struct("<d").unpack_from
+
+
+def _enc_long(out, n):
+    n = ((n << 1) ^ (n >> 63)) & 0xFFFFFFFFFFFFFFFF
+    while n > 0x7F:
+        out.append((n & 0x7F) | 0x80)
+        n >>= 7
+    out.append(n)
+
+
+def _enc_string(out, v):
+    b = v.encode("utf-8")
+    _enc_long(out, len(b))
+    out += b
+
+
+def compile_encoder(schema):
+    """Returns f(out: bytearray, value) equivalent to ``_encode(out, schema, value)``."""
+    s = schema
+    if isinstance(s, list):
+        if len(s) == 2 and s[0] == "null":            # the ubiquitous ["null", T]
+            inner = compile_encoder(s[1])
+
+            def enc_nullable(out, v):
+                if v is None:
+                    out.append(0)
+                else:
+                    out.append(2)
+                    inner(out, v)
+            return enc_nullable
+        encs = [compile_encoder(b) for b in s]
+
+        def enc_union(out, v):
+            i = _branch_of(v, s)
+            _enc_long(out, i)
+            encs[i](out, v)
+        return enc_union
+    if isinstance(s, dict):
+        t = s["type"]
+        if t == "record":
+            fields = [(f["name"], compile_encoder(f["type"]), "default" in f, f.get("default")) for f in s["fields"]]
+
+            def enc_record(out, v):
+                for name, enc, has_default, default in fields:
+                    if name in v:
+                        enc(out, v[name])
+                    elif has_default:
+                        enc(out, default)
+                    else:
+                        raise AvroError(f"missing field {name}")
+            return enc_record
+        if t == "array":
+            item = compile_encoder(s["items"])
+            fast = _is_nullable_float_array(s)
+            nullable_items = isinstance(s["items"], list)
+
+            def enc_array(out, v):
+                if fast and isinstance(v, np.ndarray):
+                    encode_float_array_fast(out, v, nullable_items)
+                    return
+                n = len(v)
+                if n:
+                    _enc_long(out, n)
+                    for x in v:
+                        item(out, x)
+                out.append(0)
+            return enc_array
+        return compile_encoder(t)
+    if s == "null":
+        return lambda out, v: None
+    if s == "boolean":
+        return lambda out, v: out.append(1 if v else 0)
+    if s in ("int", "long"):
+        return lambda out, v: _enc_long(out, int(v))
+    if s == "float":
+        return lambda out, v: out.extend(_pack_f(float(v)))
+    if s == "double":
+        return lambda out, v: out.extend(_pack_d(float(v)))
+    if s == "string":
+        return _enc_string
+    if s == "bytes":
+        def enc_bytes(out, v):
+            _enc_long(out, len(v))
+            out.extend(v)
+        return enc_bytes
+    raise AvroError(f"unsupported type {s!r}")
+
+
+def compile_decoder(schema):
+    """Returns f(buf, pos) -> (value, pos) equivalent to ``_decode(buf, pos, schema)``."""
+    s = schema
+    if isinstance(s, list):
+        decs = [compile_decoder(b) for b in s]
+        nb = len(decs)
+        if nb == 2 and s[0] == "null":
+            inner = decs[1]
+
+            def dec_nullable(buf, pos):
+                if pos >= len(buf):
+                    raise AvroError("truncated union")
+                b = buf[pos]
+                if b == 0:
+                    return None, pos + 1
+                if b == 2:
+                    return inner(buf, pos + 1)
+                raise AvroError(f"union branch {b >> 1} out of range")
+            return dec_nullable
+
+        def dec_union(buf, pos):
+            i, pos = read_long(buf, pos)
+            if not 0 <= i < nb:
+                raise AvroError(f"union branch {i} out of range")
+            return decs[i](buf, pos)
+        return dec_union
+    if isinstance(s, dict):
+        t = s["type"]
+        if t == "record":
+            fields = [(f["name"], compile_decoder(f["type"])) for f in s["fields"]]
+
+            def dec_record(buf, pos):
+                rec = {}
+                for name, dec in fields:
+                    rec[name], pos = dec(buf, pos)
+                return rec, pos
+            return dec_record
+        if t == "array":
+            if _is_nullable_float_array(s):
+                nullable_items = isinstance(s["items"], list)
+                return lambda buf, pos: decode_float_array_fast(buf, pos, nullable_items)
+            item = compile_decoder(s["items"])
+
+            def dec_array(buf, pos):
+                items = []
+                while True:
+                    n, pos = read_long(buf, pos)
+                    if n == 0:
+                        return items, pos
+                    if n < 0:
+                        n = -n
+                        _, pos = read_long(buf, pos)
+                    for _ in range(n):
+                        x, pos = item(buf, pos)
+                        items.append(x)
+            return dec_array
+        return compile_decoder(t)
+    if s == "null":
+        return lambda buf, pos: (None, pos)
+    if s in ("int", "long"):
+        return read_long
+    if s in ("string", "bytes"):
+        is_str = s == "string"
+
+        def dec_str(buf, pos):
+            n, pos = read_long(buf, pos)
+            end = pos + n
+            if n < 0 or end > len(buf):
+                raise AvroError("truncated string/bytes")
+            raw = bytes(buf[pos:end])
+            return (raw.decode("utf-8") if is_str else raw), end
+        return dec_str
+    if s == "double":
+        def dec_double(buf, pos):
+            if pos + 8 > len(buf):
+                raise AvroError("truncated double")
+            return _unpack_d(buf, pos)[0], pos + 8
+        return dec_double
+    if s == "float":
+        def dec_float(buf, pos):
+            if pos + 4 > len(buf):
+                raise AvroError("truncated float")
+            return _unpack_f(buf, pos)[0], pos + 4
+        return dec_float
+    if s == "boolean":
+        def dec_bool(buf, pos):
+            if pos >= len(buf):
+                raise AvroError("truncated boolean")
+            return buf[pos] != 0, pos + 1
+        return dec_bool
+    raise AvroError(f"unsupported type {s!r}")
+
+
+class CompiledSchema:
+    """encode(value) -> bytes / decode(buf) -> value with the closure trees built once."""
+
+    def __init__(self, schema):
+        self.schema = parse_schema(schema)
+        self._enc = compile_encoder(self.schema)
+        self._dec = compile_decoder(self.schema)
+
+    def encode(self, value, prefix: bytes = b"") -> bytes:
+        out = bytearray(prefix)
+        self._enc(out, value)
+        return bytes(out)
+
+    def decode(self, buf, pos: int = 0, require_all: bool = True):
+        v, end = self._dec(buf, pos)
+        if require_all and end != len(buf):
+            raise AvroError(f"{len(buf) - end} trailing bytes after Avro datum")
+        return v

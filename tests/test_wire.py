@@ -135,3 +135,37 @@ def test_schema_constants_are_the_reference_contract():
     assert [f["name"] for f in schemas.SEARCH_RESULTS_VALUE["fields"]] == [
         "query", "document_id_1", "chunk_1", "score_1", "document_id_2", "chunk_2", "score_2",
         "document_id_3", "chunk_3", "score_3"]
+
+
+def test_compiled_codecs_equal_the_generic_ones():
+    """The serve loop uses closure-compiled codecs; they must produce / accept exactly the generic codec's bytes."""
+    g = np.random.default_rng(1)
+    cases = [
+        (schemas.QUERIES_VALUE, {"query": "héllo wörld"}), (schemas.QUERIES_VALUE, {"query": None}),
+        (schemas.DOCUMENTS_VALUE, {"document_id": "a.md", "document_text": "t" * 300, "pages": None, "section_reference": "s",
+                                   "title": "", "fraud_categories": ["x", None], "policy_keywords": None, "char_count": -7}),
+        (schemas.QUERIES_EMBED_VALUE, {"query": "q", "embedding": g.standard_normal(1536).astype(np.float32)}),
+        (schemas.QUERIES_EMBED_VALUE, {"query": "q", "embedding": [1.0, 2.5]}),
+        (schemas.SEARCH_RESULTS_VALUE, {"query": "q", "document_id_1": "d", "chunk_1": "c", "score_1": 0.25,
+                                        "document_id_2": None, "chunk_2": None, "score_2": None,
+                                        "document_id_3": None, "chunk_3": None, "score_3": None}),
+        (schemas.RIDE_REQUESTS_VALUE, {"request_id": "r", "customer_email": "e", "pickup_zone": "p", "drop_off_zone": "d",
+                                       "price": 1.5, "number_of_passengers": 2, "request_ts": 1770605806333}),
+    ]
+    for schema, value in cases:
+        cs = avro.CompiledSchema(schema)
+        ref = avro.encode(schema, value)
+        assert cs.encode(value) == ref
+        a, b = cs.decode(ref), avro.decode(schema, ref)
+        for k in b:
+            if isinstance(b[k], np.ndarray):
+                assert (a[k] == b[k]).all()
+            else:
+                assert a[k] == b[k]
+        for bad in (ref[:-2], ref + b"\x00"):
+            with pytest.raises(avro.AvroError):
+                cs.decode(bad)
+    cs = avro.CompiledSchema(schemas.RIDE_REQUESTS_VALUE)
+    for r in fixture_records():
+        raw = base64.b64decode(r["value"])
+        assert cs.encode(cs.decode(raw, 5), prefix=raw[:5]) == raw
