@@ -294,3 +294,40 @@ def test_full_size_properties_10M(bf):
     for p in parts:
         p[2].close()
     ix.close()
+
+
+def test_c_abi_error_behaviour_on_device(bf):
+    """Error paths through the C ABI on a real device: codes and messages, no silent fallback, engine stays usable."""
+    import ctypes as C
+    import torch
+    from qsa_b200 import capi
+    from qsa_b200.engine import VectorIndex
+    ix = VectorIndex(dim=128, capacity=1000, max_batch=64, max_k=10)
+    c = bf.synth_rows(1, 0, 600, 128)
+    ix.append_bf16_bits(c)
+    lib = ix.lib
+    q = dev(bf.synth_rows(2, 0, 64, 128))
+    s = torch.empty((64, 10), dtype=torch.float32, device="cuda")
+    i = torch.empty((64, 10), dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    assert lib.sa_search(ix._h, q.data_ptr(), 65, 10, s.data_ptr(), i.data_ptr(), None, st) == capi.SA_ERR_CAPACITY
+    assert lib.sa_search(ix._h, q.data_ptr(), 64, 11, s.data_ptr(), i.data_ptr(), None, st) == capi.SA_ERR_ARG
+    assert b"max_k" in lib.sa_last_error()
+    assert lib.sa_search(ix._h, q.data_ptr() + 2, 8, 5, s.data_ptr(), i.data_ptr(), None, st) == capi.SA_ERR_ARG   # alignment
+    assert lib.sa_search(ix._h, q.data_ptr(), 8, 5, None, i.data_ptr(), None, st) == capi.SA_ERR_ARG
+    with pytest.raises(capi.SaError, match="capacity"):
+        ix.append(np.zeros((500, 128), np.float32))                      # 600 + 500 > 1000
+    assert lib.sa_corpus_commit(ix._h, 10, 5, st) == capi.SA_ERR_ARG     # commits must start at the row count
+    with pytest.raises(capi.SaError):
+        ix.set_option("cta_group", 3)
+    with pytest.raises(capi.SaError):
+        ix.set_option("no_such_option", 1)
+    h = C.c_void_p()
+    assert lib.sa_engine_create(C.byref(h), 99, 128, 1000, 64, 10) == capi.SA_ERR_ARG      # no such device
+    unbound = C.c_void_p()
+    assert lib.sa_engine_create(C.byref(unbound), 0, 128, 1000, 64, 10) == 0
+    assert lib.sa_search(unbound, q.data_ptr(), 8, 5, s.data_ptr(), i.data_ptr(), None, st) == capi.SA_ERR_ARG
+    assert b"sa_corpus_bind" in lib.sa_last_error()
+    lib.sa_engine_destroy(unbound)
+    check(ix, bf.synth_rows(2, 0, 64, 128), c, 10)                        # still healthy after all of that
+    ix.close()
