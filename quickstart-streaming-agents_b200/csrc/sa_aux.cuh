@@ -106,12 +106,17 @@ constexpr int kMaxCand = 148 * 32;  // TL * kKL upper bound
 // One block per query: (1) select the kKL best of the TL per-CTA lists by (approx score desc, row asc);
 // (2) re-score those candidates exactly -- bf16 x bf16 products are exact in fp32, the sums of products and
 // of squares run in fp64 -- so the final order equals the fp64 brute-force order; (3) sort, emit k.
+//
+// The rescoring set is kSel = 2*kKL wide: every per-CTA list keeps kKL >= k+4 entries, and the union over the TL
+// lanes is re-scored 2*kKL deep, so a wrong answer needs more than kKL-k rows of ONE lane, or more than 2*kKL-k rows
+// overall, to sit within the scan's fp32 rounding error (~1e-6 relative) of the query's k-th best score.
 template <int kKL>
 __global__ void __launch_bounds__(kMergeThreads) sa_merge_rescore_kernel(const MergeParams p) {
+  constexpr int kSel = 2 * kKL;
   __shared__ unsigned long long keys[kMaxCand];
-  __shared__ unsigned long long sel[kKL];
+  __shared__ unsigned long long sel[kSel];
   __shared__ unsigned long long wbest[kMergeThreads / 32];
-  __shared__ double cs[kKL];
+  __shared__ double cs[kSel];
   __shared__ double qq_s;
   __shared__ int nsel_s;
 
@@ -130,11 +135,12 @@ __global__ void __launch_bounds__(kMergeThreads) sa_merge_rescore_kernel(const M
     const size_t o = (cta * 128 + row) * kKL + e;
     keys[i] = make_key(p.part_score[o], p.part_idx[o]);
   }
-  if (tid == 0) nsel_s = kKL;
+  const int max_sel = min(kSel, ncand);
+  if (tid == 0) nsel_s = max_sel;
   __syncthreads();
 
-  // kKL rounds of block-wide arg-max.  Keys of real candidates are unique (rows are unique per query).
-  for (int round = 0; round < kKL; ++round) {
+  // up to kSel rounds of block-wide arg-max.  Keys of real candidates are unique (rows are unique per query).
+  for (int round = 0; round < max_sel; ++round) {
     unsigned long long best = 0;
     int pos = -1;
     for (int i = tid; i < ncand; i += kMergeThreads) {
@@ -158,10 +164,10 @@ __global__ void __launch_bounds__(kMergeThreads) sa_merge_rescore_kernel(const M
     if (pos >= 0 && best == gb && key_row(gb) >= 0) keys[pos] = 0;  // owner retires it
     if (tid == 0) {
       sel[round] = gb;
-      if (key_row(gb) < 0 && nsel_s == kKL) nsel_s = round;  // only empty slots remain
+      if (key_row(gb) < 0 && nsel_s == max_sel) nsel_s = round;  // only empty slots remain
     }
     __syncthreads();
-    if (nsel_s != kKL) break;
+    if (nsel_s != max_sel) break;
   }
   const int nsel = nsel_s;
 
@@ -214,8 +220,8 @@ __global__ void __launch_bounds__(kMergeThreads) sa_merge_rescore_kernel(const M
   __syncthreads();
 
   if (tid == 0) {
-    // insertion sort of <= kKL entries by (cosine desc, row asc)
-    int ord[kKL];
+    // insertion sort of <= kSel entries by (cosine desc, row asc)
+    int ord[kSel];
     for (int i = 0; i < nsel; ++i) {
       const double ci = cs[i];
       const int ri = key_row(sel[i]);
@@ -234,7 +240,7 @@ __global__ void __launch_bounds__(kMergeThreads) sa_merge_rescore_kernel(const M
     }
     for (int i = 0; i < p.k; ++i) {
       const size_t o = static_cast<size_t>(q) * p.k + i;
-      if (i < nsel) {
+      if (i < nsel) {  // nsel >= min(k, eligible rows): kSel > k
         p.out_score[o] = static_cast<float>(cs[ord[i]]);
         p.out_idx[o] = key_row(sel[ord[i]]);
         if (p.out_score64) p.out_score64[o] = cs[ord[i]];

@@ -331,3 +331,30 @@ def test_c_abi_error_behaviour_on_device(bf):
     lib.sa_engine_destroy(unbound)
     check(ix, bf.synth_rows(2, 0, 64, 128), c, 10)                        # still healthy after all of that
     ix.close()
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+def test_near_duplicate_cluster_does_not_break_exactness(bf, cg):
+    """Adversarial for the two-stage design: a crowd of rows that differ from the best match by one bf16 ulp in one
+    coordinate have cosines ~1e-6 apart -- the scale of the tensor-core scan's fp32 rounding -- so the scan alone cannot
+    order them; the float64 rescoring of a 2*kKL-wide candidate set must."""
+    from qsa_b200.engine import VectorIndex
+    dim, n, k = 1536, 40000, 10
+    c = bf.synth_rows(61, 0, n, dim)
+    g = np.random.default_rng(62)
+    base = c[123].copy()
+    crowd = g.choice(np.arange(1000, n), size=24, replace=False)
+    for j, r in enumerate(crowd):
+        row = base.copy()
+        col = 7 + 61 * j
+        row[col] = row[col] + (1 if j % 2 else -1)          # one ulp up or down in one coordinate
+        c[r] = row
+    q = bf.synth_queries(63, 8, dim, c)
+    q[0] = base
+    q[1] = c[crowd[3]]
+    ix = VectorIndex(dim=dim, capacity=n, max_batch=128, max_k=28)
+    ix.append_bf16_bits(c)
+    s, i = check(ix, q, c, k, cg)
+    assert i[0, 0] == 123 and set(i[0, 1:]).issubset(set(crowd.tolist()))
+    check(ix, q, c, 20, cg)                                  # 32-entry lists, 64-wide rescoring
+    ix.close()
