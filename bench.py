@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--cta-group", type=int, default=0, help="0 auto, 1, 2")
+    ap.add_argument("--no-share", action="store_true", help="disable cross-lane threshold sharing")
+    ap.add_argument("--list-len", type=int, default=0, help="candidate list length (0 auto, 16, 32)")
     ap.add_argument("--pace-gain", type=int, default=-1, help="drift-control gain (-1 = engine default, 0 = off)")
     ap.add_argument("--recall-queries", type=int, default=8, help="queries checked against numpy over ALL rows")
     ap.add_argument("--cpu-sample-queries", type=int, default=256)
@@ -215,6 +217,10 @@ def run_b200(a):
         ix.set_option("cta_group", a.cta_group)
     if a.pace_gain >= 0:
         ix.set_option("pace_gain", a.pace_gain)
+    if a.list_len:
+        ix.set_option("list_len", a.list_len)
+    if a.no_share:
+        ix.set_option("share_thresholds", 0)
     fill_corpus(ix, n_local, dim, seed=1234 + rank)
     g = torch.Generator(device="cuda").manual_seed(4321)
     q_f32 = torch.randn((B, dim), generator=g, device="cuda", dtype=torch.float32)

@@ -102,6 +102,8 @@ struct sa_engine {
   long long* dbg_times = nullptr;  // [num_sms][2] CTA start/end timestamps of the last scan launch (option "record_times")
   int opt_record_times = 0;
   int last_grid = 0;
+  unsigned* thr_shared = nullptr;  // [num_sms * 128] shared per-query thresholds of one scan launch (zeroed per launch)
+  int opt_share_thresholds = 1;
   int* lane_progress = nullptr;  // [num_sms] lockstep counters of the scan (zeroed per launch)
 
   // options
@@ -111,6 +113,7 @@ struct sa_engine {
   int opt_pace_gain = -1;  // -1 = auto (16 cycles/tile for CTA pairs, 32 for single CTAs), 0 = off
   int opt_pace_max = -1;   // -1 = auto (8 x gain)
   int opt_unit_map = 0;
+  int opt_list_len = 0;   // 0 = auto (16 when k <= 12, else 32)
 
   // timing: CUDA events of the most recent kTimingRing searches
   struct Timing {
@@ -241,7 +244,8 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
   if (reinterpret_cast<uintptr_t>(q_bf16) % 16) return fail(SA_ERR_ARG, "query buffer must be 16-byte aligned");
   SA_CUDA(cudaSetDevice(e->device));
 
-  const int kl = (k + 4 <= 16) ? 16 : 32;
+  const int kl = e->opt_list_len ? e->opt_list_len : ((k + 4 <= 16) ? 16 : 32);
+  if (k + 4 > kl) return fail(SA_ERR_ARG, "k %d needs candidate lists longer than list_len %d", k, kl);
   const int64_t n_rows = e->n_rows;
   const int num_tiles = static_cast<int>((n_rows + sa::kBlockN - 1) / sa::kBlockN);
   const int cg = choose_cg(e, nq);
@@ -282,6 +286,11 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
       sp.lane_progress = e->lane_progress;
       sp.pace_gain = gain;
       SA_CUDA(cudaMemsetAsync(e->lane_progress, 0, sizeof(int) * lp.nqb * lp.tl, st));
+    }
+    sp.thr_shared = nullptr;
+    if (e->opt_share_thresholds && lp.tl > 1) {
+      sp.thr_shared = e->thr_shared;
+      SA_CUDA(cudaMemsetAsync(e->thr_shared, 0, sizeof(unsigned) * lp.nqb * 128 * lp.cg, st));
     }
     sp.dbg_dots = nullptr;
     sp.dbg_tile = -1;
@@ -399,6 +408,7 @@ int sa_engine_create(sa_engine** out, int device, int dim, int64_t capacity_rows
   // a blocking stream: ordered after work already queued on the legacy default stream (torch's default)
   SA_TRY(cudaStreamCreate(&e->own_stream));
   SA_TRY(cudaMalloc(&e->lane_progress, sizeof(int) * e->num_sms));
+  SA_TRY(cudaMalloc(&e->thr_shared, sizeof(unsigned) * e->num_sms * 128));
   SA_TRY(cudaMalloc(&e->dbg_times, sizeof(long long) * 2 * e->num_sms));
   for (int r = 0; r < kTimingRing; ++r)
     for (int i = 0; i < kMaxLaunches; ++i) e->ring[r].ev_scan[i][0] = e->ring[r].ev_scan[i][1] = nullptr;
@@ -432,6 +442,7 @@ void sa_engine_destroy(sa_engine* e) {
   cudaFreeHost(e->h_stage);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   cudaFree(e->lane_progress);
+  cudaFree(e->thr_shared);
   cudaFree(e->dbg_times);
   for (int r = 0; r < kTimingRing; ++r) {
     for (int i = 0; i < 2; ++i)
@@ -664,6 +675,15 @@ int sa_set_option(sa_engine* e, const char* name, int64_t value) {
     e->opt_max_launch_qblocks = static_cast<int>(value);
     return SA_OK;
   }
+  if (!strcmp(name, "share_thresholds")) {
+    e->opt_share_thresholds = value ? 1 : 0;
+    return SA_OK;
+  }
+  if (!strcmp(name, "list_len")) {
+    if (value != 0 && value != 16 && value != 32) return fail(SA_ERR_ARG, "list_len must be 0, 16 or 32");
+    e->opt_list_len = static_cast<int>(value);
+    return SA_OK;
+  }
   if (!strcmp(name, "record_times")) {
     e->opt_record_times = value ? 1 : 0;
     return SA_OK;
@@ -736,6 +756,7 @@ int sa_debug_tile_dots(sa_engine* e, const void* q_bf16_dev, int nq, int tile, i
   sp.pace_gain = 0;
   sp.pace_max = 0;
   sp.unit_map = 0;
+  sp.thr_shared = nullptr;
   sp.dbg_times = nullptr;
   sp.dbg_dots = out_dots_dev;
   sp.dbg_tile = tile;

@@ -107,9 +107,11 @@ constexpr int kMaxCand = 148 * 32;  // TL * kKL upper bound
 // (2) re-score those candidates exactly -- bf16 x bf16 products are exact in fp32, the sums of products and
 // of squares run in fp64 -- so the final order equals the fp64 brute-force order; (3) sort, emit k.
 //
-// The rescoring set is kSel = 2*kKL wide: every per-CTA list keeps kKL >= k+4 entries, and the union over the TL
-// lanes is re-scored 2*kKL deep, so a wrong answer needs more than kKL-k rows of ONE lane, or more than 2*kKL-k rows
-// overall, to sit within the scan's fp32 rounding error (~1e-6 relative) of the query's k-th best score.
+// The rescoring set is kSel = 2*kKL wide.  What is guaranteed: every tile lane keeps its kKL >= k+4 best rows whose
+// approximate score reaches the shared threshold, and that threshold never exceeds the query's global kKL-th best
+// approximate score; so the union always contains the global approximate top-kKL, and usually (the shared threshold
+// sits near the global (kKL*TL)-th best) the top-2*kKL as well.  A wrong answer therefore needs more than kKL-k rows
+// (6 at k = 10) within the scan's fp32 rounding error (~1e-6 relative) of the query's k-th best score.
 template <int kKL>
 __global__ void __launch_bounds__(kMergeThreads) sa_merge_rescore_kernel(const MergeParams p) {
   constexpr int kSel = 2 * kKL;

@@ -54,10 +54,28 @@ struct ScanParams {
   int max_drift;          // lead (in tiles) over the slowest lane-mate that is not paced
   int pace_gain;          // SM cycles of delay per K-slice issue per tile of lead beyond max_drift (0 = free-running)
   int pace_max;           // cap of that delay
+  unsigned* thr_shared;   // [nqb*128*kCG] per-query lower bound on the kKL-th best score, order-preserving keys
+                          // (zeroed before launch), or nullptr: lanes then learn their thresholds alone
   long long* dbg_times;   // optional [gridDim.x][2]: globaltimer at CTA start / end (ns), for drift studies
   float* dbg_dots;        // debug builds only: raw accumulators of (unit 0 .. nqb-1, tile dbg_tile) [nqb*128*kCG][256]
   int dbg_tile;
 };
+
+// Order-preserving float <-> unsigned key (larger float <=> larger key; key 0 is below every float).
+__device__ __forceinline__ unsigned float_to_key(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+// The largest float strictly less than x (x finite): `s > float_below(x)` <=> `s >= x`.
+__device__ __forceinline__ float float_below(float x) {
+  const int b = __float_as_int(x);
+  if (x > 0.f) return __int_as_float(b - 1);
+  if (x < 0.f) return __int_as_float(b + 1);
+  return __int_as_float(static_cast<int>(0x80000001u));  // below +-0: the smallest negative denormal
+}
 
 // Sorted (descending score, ascending row on ties) insertion into a register-resident list.
 // Precondition: s > sc[kKL-1].  Rows reach a thread in ascending order, so a strict compare keeps the
@@ -232,6 +250,16 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       id[i] = -1;
     }
     float thr = -INFINITY;
+    // Threshold sharing.  A thread's list only ever sees its own tile lane, so alone it needs ~kKL*ln(n) insertions
+    // to warm up, and a warp pays for every lane's insertions.  But if ANY lane already holds kKL rows scoring >= x
+    // for this query, no row scoring < x can be in the query's global top-kKL.  So each epilogue thread publishes its
+    // kKL-th best (atomicMax on an order-preserving key) and reads the shared bound once per tile: every lane gets the
+    // threshold of the whole machine's progress, and the warm-up tail disappears.  The shared bound admits ties
+    // (>=), the thread's own bound stays strict (>), so tie-breaking by row is unchanged.
+    const int q_in_launch = qb * (kBlockM * kCG) + static_cast<int>(rank) * kBlockM + et;
+    unsigned* thr_slot = (p.thr_shared != nullptr && q_in_launch < p.nq) ? p.thr_shared + q_in_launch : nullptr;
+    float thr_floor = -INFINITY;  // largest float strictly below the shared bound
+    float published = -INFINITY;
 
     auto load_ic = [&](int t, float& x0, float& x1) {
       const long long r0 = static_cast<long long>(t) * kBlockN + 2 * et;
@@ -251,6 +279,13 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       const float qnan = __int_as_float(0x7fc00000);
       reinterpret_cast<float2*>(ic)[et] = make_float2(n0 > 0.f ? n0 : qnan, n1 > 0.f ? n1 : qnan);
       if (t + TL < p.num_tiles) load_ic(t + TL, n0, n1);
+      if (thr_slot != nullptr) {
+        const unsigned key = ld_relaxed_gpu_u32(thr_slot);
+        if (key != 0u) {
+          thr_floor = float_below(key_to_float(key));
+          thr = fmaxf(thr, thr_floor);
+        }
+      }
       asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue-only named barrier: ic[] visible
 
       mbar_wait(tfull_bar(a), aph);
@@ -283,7 +318,7 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           while (m > thr) {  // rare after warm-up: ~kKL/n per value
             const int j = (s0 == m) ? 0 : (s1 == m) ? 1 : (s2 == m) ? 2 : 3;  // lowest row among equals first
             list_insert<kKL>(sc, id, m, row0 + c * 32 + g * 4 + j);
-            thr = sc[kKL - 1];
+            thr = fmaxf(sc[kKL - 1], thr_floor);
             s0 = (j == 0) ? -INFINITY : s0;
             s1 = (j == 1) ? -INFINITY : s1;
             s2 = (j == 2) ? -INFINITY : s2;
@@ -294,6 +329,10 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
+      if (thr_slot != nullptr && sc[kKL - 1] > published) {  // list full and its tail improved: tell the others
+        published = sc[kKL - 1];
+        atomicMax(thr_slot, float_to_key(published));
+      }
       if (lane == 0) {
         if constexpr (kCG == 1)
           mbar_arrive(tempty_bar(a));

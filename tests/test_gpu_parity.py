@@ -347,14 +347,20 @@ def test_near_duplicate_cluster_does_not_break_exactness(bf, cg):
     for j, r in enumerate(crowd):
         row = base.copy()
         col = 7 + 61 * j
-        row[col] = row[col] + (1 if j % 2 else -1)          # one ulp up or down in one coordinate
+        row[col] = np.uint16(int(row[col]) + (1 if j % 2 else -1))   # one ulp up or down in one coordinate
         c[r] = row
     q = bf.synth_queries(63, 8, dim, c)
-    q[0] = base
-    q[1] = c[crowd[3]]
+    bf32 = bf.bf16_bits_to_f32(base)
+    for r in (0, 1):     # queries NEAR the crowd (not on it: at the exact maximum the differences are second order)
+        q[r] = bf.f32_to_bf16_bits(bf32 + np.float32(0.1 * np.abs(bf32).mean()) * g.standard_normal(dim).astype(np.float32))
+    rs, ri = bf.cosine_topk_f64(q[:2], c, 25)
+    gaps = np.abs(np.diff(rs, axis=1))
+    assert gaps.min() > 1e-13 and np.median(gaps) < 1e-7     # resolvable in float64, far below fp32 resolution
+    s3, i3 = bf.cosine_topk_sgemm(q[:2], [(0, c)], k)
+    assert (i3 != ri[:, :k]).any()                             # an fp32-only ranking really does get this wrong
     ix = VectorIndex(dim=dim, capacity=n, max_batch=128, max_k=28)
     ix.append_bf16_bits(c)
     s, i = check(ix, q, c, k, cg)
-    assert i[0, 0] == 123 and set(i[0, 1:]).issubset(set(crowd.tolist()))
+    assert set(i[0]).issubset(set(crowd.tolist()) | {123})
     check(ix, q, c, 20, cg)                                  # 32-entry lists, 64-wide rescoring
     ix.close()
