@@ -25,7 +25,13 @@ import sys
 import threading
 import time
 
-import numpy as np
+# torchrun exports OMP_NUM_THREADS=1 to its children; the CPU arm must be allowed every host thread, and OpenBLAS
+# sizes its pool from the environment when numpy is first imported -- so fix the environment before that import.
+if "reference" in sys.argv and os.environ.get("RANK", "0") == "0":
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -72,6 +78,24 @@ def measured_peaks():
 # ----------------------------------------------------------------------------------------------------
 # CPU arm (oracle; the only place besides tests/ and smoke() that touches oracle/)
 # ----------------------------------------------------------------------------------------------------
+def blas_all_threads():
+    """Context manager: let numpy's BLAS use every host thread (torchrun exports OMP_NUM_THREADS=1 to its children,
+    which would otherwise cripple the CPU arm).  Yields the thread count actually in effect."""
+    import contextlib
+
+    @contextlib.contextmanager
+    def cm():
+        n = os.cpu_count() or 1
+        try:
+            from threadpoolctl import threadpool_info, threadpool_limits
+            with threadpool_limits(limits=n):
+                got = [p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"]
+                yield max(got) if got else n
+        except ImportError:
+            yield int(os.environ.get("OMP_NUM_THREADS", n))
+    return cm()
+
+
 def cpu_sample_run(q_bits, prepared, k, full_rows):
     """Time numpy brute force on (queries x sample rows) over a corpus already resident in RAM as unit-norm fp32
     rows (ingest-time work, like the GPU engine's inverse norms, is not timed).  Returns (qps scaled to
@@ -99,14 +123,14 @@ def run_reference(a):
     q = bf.synth_queries(4321, nq, a.dim, chunks[0][1])
     prepared = bf.prepare_chunks_f32(chunks)
     vals = []
-    for _ in range(a.warmup):
-        cpu_sample_run(q[: max(8, nq // 8)], prepared[:1], a.k, a.rows)
-    t0 = time.perf_counter()
-    for _ in range(a.steps):
-        vals.append(cpu_sample_run(q, prepared, a.k, a.rows)[0])
-    dt = time.perf_counter() - t0
+    with blas_all_threads() as cores:
+        for _ in range(a.warmup):
+            cpu_sample_run(q[: max(8, nq // 8)], prepared[:1], a.k, a.rows)
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            vals.append(cpu_sample_run(q, prepared, a.k, a.rows)[0])
+        dt = time.perf_counter() - t0
     v = float(np.median(vals))
-    cores = os.cpu_count()
     sample = f"{nq} queries x {rows} rows per step (of {a.batch} x {a.rows}); QPS scaled by rows"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
@@ -370,9 +394,10 @@ def run_b200(a):
         nsq = min(a.cpu_sample_queries, B)
         qs = q_bf16[:nsq].view(torch.int16).cpu().numpy().view(np.uint16)
         prepared = bf.prepare_chunks_f32(dev_chunks(a.cpu_sample_rows))
-        cpu_sample_run(qs[:16], prepared[:1], k, n_total)  # warm BLAS threads
-        v, dt = cpu_sample_run(qs, prepared, k, n_total)
-        result["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+        with blas_all_threads() as cores:
+            cpu_sample_run(qs[:16], prepared[:1], k, n_total)  # warm BLAS threads
+            v, dt = cpu_sample_run(qs, prepared, k, n_total)
+        result["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                   "sample": f"{nsq} queries x {sum(len(c) for _, c, _ in prepared)} rows in {dt:.1f}s "
                                             f"(numpy fp32 sgemm brute force over unit-norm fp32 rows in RAM, "
                                             f"QPS scaled to {n_total} rows)"}
