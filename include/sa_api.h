@@ -104,6 +104,7 @@ int sa_timing_mean(sa_engine* e, int n, float* scan_ms_mean, float* total_ms_mea
  * drift control between query blocks that share corpus tiles (keeps a shared tile L2-resident so it crosses HBM
  * once): "max_drift" = unpaced lead in tiles (default 1), "pace_gain" = delay cycles per K-slice per extra tile
  * of lead (-1 auto, 0 off), "pace_max" = cap of that delay (-1 auto);
+ * "qpu2" = 1 | 0 (let a unit carry two query blocks when that fills more SMs; default 1),
  * "share_thresholds" = 1 | 0 (tile lanes exchange per-query top-k thresholds; default 1), "list_len" = 0 (auto) | 16 | 32,
  * "unit_map" = 0 | 1 (CTA -> (query block, tile lane) mapping), "record_times" = 0 | 1 (per-CTA timestamps). */
 int sa_set_option(sa_engine* e, const char* name, int64_t value);
@@ -115,9 +116,10 @@ int sa_debug_tile_dots(sa_engine* e, const void* q_bf16_dev, int nq, int tile, i
                        uintptr_t stream);
 
 /* Test hook (pure host logic, no GPU needed): how a batch of nq queries is split into scan launches on a device
- * with num_sms SMs.  out receives up to max_out rows of {first query, queries, query blocks, tile lanes}. */
-int sa_debug_plan(int num_sms, int nq, int cta_group, int num_tiles, int max_launch_qblocks, int* out, int max_out,
-                  int* n_launches);
+ * with num_sms SMs.  out receives up to max_out rows of {first query, queries, query blocks, tile lanes,
+ * query blocks per unit}. */
+int sa_debug_plan(int num_sms, int nq, int cta_group, int num_tiles, int max_launch_qblocks, int allow_qpu2, int* out,
+                  int max_out, int* n_launches);
 
 /* Pinned host memory for callers that want truly asynchronous staging. */
 int sa_host_alloc(void** out, uint64_t bytes);

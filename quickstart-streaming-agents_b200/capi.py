@@ -74,7 +74,7 @@ def load() -> C.CDLL:
         "sa_set_option": (i32, [vp, C.c_char_p, i64]),
         "sa_get_info": (i32, [vp, C.c_char_p, C.POINTER(i64)]),
         "sa_debug_tile_dots": (i32, [vp, vp, i32, i32, i32, vp, vp]),
-        "sa_debug_plan": (i32, [i32, i32, i32, i32, i32, C.POINTER(i32), i32, C.POINTER(i32)]),
+        "sa_debug_plan": (i32, [i32, i32, i32, i32, i32, i32, C.POINTER(i32), i32, C.POINTER(i32)]),
         "sa_host_alloc": (i32, [C.POINTER(vp), u64]),
         "sa_host_free": (i32, [vp]),
     }

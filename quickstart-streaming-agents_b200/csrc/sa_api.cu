@@ -113,6 +113,7 @@ struct sa_engine {
   int opt_pace_gain = -1;  // -1 = auto (16 cycles/tile for CTA pairs, 32 for single CTAs), 0 = off
   int opt_pace_max = -1;   // -1 = auto (8 x gain)
   int opt_unit_map = 0;
+  int opt_qpu2 = 1;       // allow two query blocks per unit when that fills more SMs
   int opt_list_len = 0;   // 0 = auto (16 when k <= 12, else 32)
 
   // timing: CUDA events of the most recent kTimingRing searches
@@ -135,12 +136,33 @@ struct LaunchPlan {
   int nq;   // queries in this launch
   int nqb;  // query blocks (of 128*cg)
   int tl;   // tile lanes
+  int qpu;  // query blocks per unit (1, or 2: two passes per tile, two candidate lists per thread)
 };
+
+// Tile lanes and walk length of one launch holding `per` query blocks.
+void lanes_for(int units, int per, int num_tiles, int qpu2_mode, int* tl, int* qpu, long* cost) {
+  const int tl1 = std::max(1, std::min(units / per, num_tiles));
+  const long cost1 = (num_tiles + tl1 - 1) / tl1;
+  *tl = tl1;
+  *qpu = 1;
+  *cost = cost1;
+  if (qpu2_mode != 0 && per >= 2) {  // 0 never, 1 when it pays, 2 always (tests)
+    const int nslots = (per + 1) / 2;
+    const int tl2 = std::max(1, std::min(units / nslots, num_tiles));
+    const long cost2 = 2L * ((num_tiles + tl2 - 1) / tl2);
+    if (qpu2_mode == 2 || cost2 * 100 < cost1 * 99) {  // two passes per tile must buy more than 1 %
+      *tl = tl2;
+      *qpu = 2;
+      *cost = cost2;
+    }
+  }
+}
 
 // Split the batch into scan launches.  A launch with nqb query blocks runs TL = floor(units / nqb) tile
 // lanes, each walking ceil(num_tiles / TL) tiles; pick the split that minimises the summed tile walks
 // (fewer launches win ties: every launch re-streams the corpus through HBM once).
-std::vector<LaunchPlan> plan_search(int num_sms, int max_launch_qblocks, int nq, int cg, int num_tiles) {
+std::vector<LaunchPlan> plan_search(int num_sms, int max_launch_qblocks, int nq, int cg, int num_tiles,
+                                    int allow_qpu2) {
   const int rows_per_qb = 128 * cg;
   const int units = num_sms / cg;
   const int nqb_total = (nq + rows_per_qb - 1) / rows_per_qb;
@@ -154,8 +176,10 @@ std::vector<LaunchPlan> plan_search(int num_sms, int max_launch_qblocks, int nq,
     int left = nqb_total;
     for (int i = 0; i < l; ++i) {
       const int per = (left + (l - i) - 1) / (l - i);
-      const int tl = std::max(1, std::min(units / per, num_tiles));
-      cost += (num_tiles + tl - 1) / tl;
+      int tl, qpu;
+      long c;
+      lanes_for(units, per, num_tiles, allow_qpu2, &tl, &qpu, &c);
+      cost += c;
       left -= per;
     }
     if (best_cost < 0 || cost * 100 < best_cost * 97) {  // a later (more launches) split must win by > 3 %
@@ -168,11 +192,12 @@ std::vector<LaunchPlan> plan_search(int num_sms, int max_launch_qblocks, int nq,
   for (int i = 0; i < best_l; ++i) {
     const int per = (left + (best_l - i) - 1) / (best_l - i);
     LaunchPlan lp;
+    long c;
     lp.cg = cg;
     lp.q0 = qb0 * rows_per_qb;
     lp.nq = std::min(nq - lp.q0, per * rows_per_qb);
     lp.nqb = per;
-    lp.tl = std::max(1, std::min(units / per, num_tiles));
+    lanes_for(units, per, num_tiles, allow_qpu2, &lp.tl, &lp.qpu, &c);
     out.push_back(lp);
     qb0 += per;
     left -= per;
@@ -180,9 +205,9 @@ std::vector<LaunchPlan> plan_search(int num_sms, int max_launch_qblocks, int nq,
   return out;
 }
 
-template <int kCG, int kKL, bool kDebug>
+template <int kCG, int kKL, int kQPU, bool kDebug>
 int launch_scan(const CUtensorMap& tq, const CUtensorMap& tc, const sa::ScanParams& p, int grid, cudaStream_t st) {
-  auto kern = sa::sa_scan_kernel<kCG, kKL, kDebug>;
+  auto kern = sa::sa_scan_kernel<kCG, kKL, kQPU, kDebug>;
   // per-device attribute; a few microseconds, so set it on every launch rather than caching per device
   SA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, sa::ScanCfg<kCG>::kSmemBytes));
   cudaLaunchConfig_t cfg = {};
@@ -201,17 +226,19 @@ int launch_scan(const CUtensorMap& tq, const CUtensorMap& tc, const sa::ScanPara
   return SA_OK;
 }
 
-int launch_scan_dispatch(int cg, int kl, bool debug, const CUtensorMap& tq, const CUtensorMap& tc,
+int launch_scan_dispatch(int cg, int kl, int qpu, bool debug, const CUtensorMap& tq, const CUtensorMap& tc,
                          const sa::ScanParams& p, int grid, cudaStream_t st) {
   if (debug) {
-    if (cg == 1) return launch_scan<1, 16, true>(tq, tc, p, grid, st);
-    return launch_scan<2, 16, true>(tq, tc, p, grid, st);
+    if (cg == 1) return launch_scan<1, 16, 1, true>(tq, tc, p, grid, st);
+    return launch_scan<2, 16, 1, true>(tq, tc, p, grid, st);
   }
-  if (cg == 1 && kl == 16) return launch_scan<1, 16, false>(tq, tc, p, grid, st);
-  if (cg == 1 && kl == 32) return launch_scan<1, 32, false>(tq, tc, p, grid, st);
-  if (cg == 2 && kl == 16) return launch_scan<2, 16, false>(tq, tc, p, grid, st);
-  if (cg == 2 && kl == 32) return launch_scan<2, 32, false>(tq, tc, p, grid, st);
-  return fail(SA_ERR_ARG, "no scan instantiation for cta_group %d list %d", cg, kl);
+  if (cg == 1 && kl == 16 && qpu == 1) return launch_scan<1, 16, 1, false>(tq, tc, p, grid, st);
+  if (cg == 1 && kl == 16 && qpu == 2) return launch_scan<1, 16, 2, false>(tq, tc, p, grid, st);
+  if (cg == 1 && kl == 32 && qpu == 1) return launch_scan<1, 32, 1, false>(tq, tc, p, grid, st);
+  if (cg == 2 && kl == 16 && qpu == 1) return launch_scan<2, 16, 1, false>(tq, tc, p, grid, st);
+  if (cg == 2 && kl == 16 && qpu == 2) return launch_scan<2, 16, 2, false>(tq, tc, p, grid, st);
+  if (cg == 2 && kl == 32 && qpu == 1) return launch_scan<2, 32, 1, false>(tq, tc, p, grid, st);
+  return fail(SA_ERR_ARG, "no scan instantiation for cta_group %d list %d qpu %d", cg, kl, qpu);
 }
 
 int choose_cg(const sa_engine* e, int nq) {
@@ -249,7 +276,8 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
   const int64_t n_rows = e->n_rows;
   const int num_tiles = static_cast<int>((n_rows + sa::kBlockN - 1) / sa::kBlockN);
   const int cg = choose_cg(e, nq);
-  std::vector<LaunchPlan> plan = plan_search(e->num_sms, e->opt_max_launch_qblocks, nq, cg, std::max(num_tiles, 1));
+  std::vector<LaunchPlan> plan = plan_search(e->num_sms, e->opt_max_launch_qblocks, nq, cg, std::max(num_tiles, 1),
+                                             kl == 16 ? e->opt_qpu2 : 0);
   if (static_cast<int>(plan.size()) > kMaxLaunches)
     return fail(SA_ERR_CAPACITY, "batch needs %zu scan launches (max %d)", plan.size(), kMaxLaunches);
 
@@ -274,7 +302,7 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
     sp.tl_count = lp.tl;
     sp.part_score = e->part_score;
     sp.part_idx = e->part_idx;
-    sp.corpus_evict_first = (lp.nqb == 1) ? 1 : 0;
+    sp.corpus_evict_first = (lp.nqb == 1) ? 1 : 0;  // a tile nobody else will ask for: stream it through L2
     sp.lane_progress = nullptr;
     sp.max_drift = e->opt_max_drift;
     sp.pace_gain = 0;
@@ -282,10 +310,11 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
     sp.unit_map = e->opt_unit_map;
     const int gain = e->opt_pace_gain >= 0 ? e->opt_pace_gain : (lp.cg == 2 ? 16 : 32);
     sp.pace_max = e->opt_pace_max >= 0 ? e->opt_pace_max : 8 * gain;
-    if (lp.nqb > 1 && gain > 0) {
+    const int nslots = (lp.nqb + lp.qpu - 1) / lp.qpu;  // units per tile lane
+    if (nslots > 1 && gain > 0) {
       sp.lane_progress = e->lane_progress;
       sp.pace_gain = gain;
-      SA_CUDA(cudaMemsetAsync(e->lane_progress, 0, sizeof(int) * lp.nqb * lp.tl, st));
+      SA_CUDA(cudaMemsetAsync(e->lane_progress, 0, sizeof(int) * nslots * lp.tl, st));
     }
     sp.thr_shared = nullptr;
     if (e->opt_share_thresholds && lp.tl > 1) {
@@ -295,11 +324,11 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
     sp.dbg_dots = nullptr;
     sp.dbg_tile = -1;
     sp.dbg_times = e->opt_record_times ? e->dbg_times : nullptr;
-    const int grid = lp.nqb * lp.tl * lp.cg;
+    const int grid = nslots * lp.tl * lp.cg;
     e->last_grid = grid;
 
     SA_CUDA(cudaEventRecord(tm.ev_scan[li][0], st));
-    rc = launch_scan_dispatch(lp.cg, kl, false, tq, e->tmap_c[lp.cg - 1], sp, grid, st);
+    rc = launch_scan_dispatch(lp.cg, kl, lp.qpu, false, tq, e->tmap_c[lp.cg - 1], sp, grid, st);
     if (rc) return rc;
     SA_CUDA(cudaEventRecord(tm.ev_scan[li][1], st));
 
@@ -314,6 +343,7 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
     mp.cg = lp.cg;
     mp.nqb = lp.nqb;
     mp.tl_count = lp.tl;
+    mp.qpu = lp.qpu;
     mp.unit_map = e->opt_unit_map;
     mp.out_score = out_score + static_cast<size_t>(lp.q0) * k;
     mp.out_idx = out_idx + static_cast<size_t>(lp.q0) * k;
@@ -675,6 +705,11 @@ int sa_set_option(sa_engine* e, const char* name, int64_t value) {
     e->opt_max_launch_qblocks = static_cast<int>(value);
     return SA_OK;
   }
+  if (!strcmp(name, "qpu2")) {
+    if (value < 0 || value > 2) return fail(SA_ERR_ARG, "qpu2 must be 0 (never), 1 (auto) or 2 (always)");
+    e->opt_qpu2 = static_cast<int>(value);
+    return SA_OK;
+  }
   if (!strcmp(name, "share_thresholds")) {
     e->opt_share_thresholds = value ? 1 : 0;
     return SA_OK;
@@ -760,22 +795,24 @@ int sa_debug_tile_dots(sa_engine* e, const void* q_bf16_dev, int nq, int tile, i
   sp.dbg_times = nullptr;
   sp.dbg_dots = out_dots_dev;
   sp.dbg_tile = tile;
-  return launch_scan_dispatch(cta_group, 16, true, tq, e->tmap_c[cta_group - 1], sp, nqb * cta_group,
+  return launch_scan_dispatch(cta_group, 16, 1, true, tq, e->tmap_c[cta_group - 1], sp, nqb * cta_group,
                               reinterpret_cast<cudaStream_t>(stream));
 }
 
-int sa_debug_plan(int num_sms, int nq, int cta_group, int num_tiles, int max_launch_qblocks, int* out, int max_out,
-                  int* n_launches) {
+int sa_debug_plan(int num_sms, int nq, int cta_group, int num_tiles, int max_launch_qblocks, int allow_qpu2, int* out,
+                  int max_out, int* n_launches) {
   if (!out || !n_launches) return fail(SA_ERR_ARG, "null argument");
   if (num_sms < 2 || nq <= 0 || num_tiles < 0 || (cta_group != 1 && cta_group != 2))
     return fail(SA_ERR_ARG, "bad planning input");
-  std::vector<LaunchPlan> plan = plan_search(num_sms, max_launch_qblocks, nq, cta_group, std::max(num_tiles, 1));
+  std::vector<LaunchPlan> plan =
+      plan_search(num_sms, max_launch_qblocks, nq, cta_group, std::max(num_tiles, 1), allow_qpu2);
   if (static_cast<int>(plan.size()) > max_out) return fail(SA_ERR_CAPACITY, "plan has %zu launches", plan.size());
   for (size_t i = 0; i < plan.size(); ++i) {
-    out[4 * i + 0] = plan[i].q0;
-    out[4 * i + 1] = plan[i].nq;
-    out[4 * i + 2] = plan[i].nqb;
-    out[4 * i + 3] = plan[i].tl;
+    out[5 * i + 0] = plan[i].q0;
+    out[5 * i + 1] = plan[i].nq;
+    out[5 * i + 2] = plan[i].nqb;
+    out[5 * i + 3] = plan[i].tl;
+    out[5 * i + 4] = plan[i].qpu;
   }
   *n_launches = static_cast<int>(plan.size());
   return SA_OK;

@@ -84,7 +84,7 @@ __device__ __forceinline__ unsigned long long make_key(float s, int row) {
 __device__ __forceinline__ int key_row(unsigned long long k) { return static_cast<int>(~static_cast<uint32_t>(k)); }
 
 struct MergeParams {
-  const float* part_score;  // [grid CTAs][128][kKL] from the scan
+  const float* part_score;  // [grid CTAs][128][qpu][kKL] from the scan
   const int* part_idx;
   const uint16_t* corpus;   // [capacity][dim] bf16
   const uint16_t* queries;  // [nq][dim] bf16 (this launch's queries)
@@ -94,6 +94,7 @@ struct MergeParams {
   int cg;                   // CTAs per unit in the scan that produced the lists
   int nqb;
   int tl_count;
+  int qpu;                  // query blocks per unit in that scan (lists per CTA row)
   int unit_map;             // same mapping switch as ScanParams::unit_map
   float* out_score;         // [nq][k] fp32 cosine
   int* out_idx;             // [nq][k] shard-local row, -1 when fewer than k rows qualify
@@ -132,9 +133,11 @@ __global__ void __launch_bounds__(kMergeThreads) sa_merge_rescore_kernel(const M
 
   for (int i = tid; i < ncand; i += kMergeThreads) {
     const int tl = i / kKL, e = i % kKL;
-    const int unit = p.unit_map == 0 ? tl * p.nqb + qb : qb * p.tl_count + tl;
+    const int nslots = (p.nqb + p.qpu - 1) / p.qpu;
+    const int slot = qb / p.qpu, pass = qb % p.qpu;
+    const int unit = p.unit_map == 0 ? tl * nslots + slot : slot * p.tl_count + tl;
     const size_t cta = static_cast<size_t>(unit) * p.cg + cta_in_unit;
-    const size_t o = (cta * 128 + row) * kKL + e;
+    const size_t o = ((cta * 128 + row) * p.qpu + pass) * kKL + e;
     keys[i] = make_key(p.part_score[o], p.part_idx[o]);
   }
   const int max_sel = min(kSel, ncand);

@@ -221,6 +221,31 @@ def test_full_size_properties_1M(bf):
     ix.close()
 
 
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("n,dim,nq,k", [
+    (30000, 128, 1100, 10),     # several launches / odd number of query blocks (last unit carries one block)
+    (70000, 256, 512, 12),      # exactly two pair blocks
+    (5000, 1536, 300, 3),       # ragged batch, few tiles
+])
+def test_two_query_blocks_per_unit(bf, cg, n, dim, nq, k):
+    """kQPU = 2: a unit makes two passes per tile and keeps two candidate lists; forced on (qpu2 = 2), off (0) and
+    automatic (1) must all agree with the oracle."""
+    from qsa_b200.engine import VectorIndex
+    c = bf.synth_rows(71, 0, n, dim)
+    c[n // 2] = c[9]
+    q = bf.synth_queries(72, nq, dim, c)
+    q[0] = c[9]
+    ix = VectorIndex(dim=dim, capacity=n, max_batch=2048, max_k=12)
+    ix.append_bf16_bits(c)
+    for mode in (2, 0, 1):
+        ix.set_option("qpu2", mode)
+        check(ix, q, c, k, cg)
+    ix.set_option("qpu2", 2)
+    ix.set_option("unit_map", 1)
+    check(ix, q, c, k, cg)
+    ix.close()
+
+
 def test_drift_control_and_mapping_options_do_not_change_answers(bf):
     """Pacing, unit mapping and CTA grouping only move work around in time and space."""
     from qsa_b200.engine import VectorIndex
