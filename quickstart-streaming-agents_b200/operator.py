@@ -23,6 +23,19 @@ from dataclasses import dataclass, field
 import numpy as np
 
 
+def _avro_nullable_string(v: str | None) -> bytes:
+    if v is None:
+        return b"\x00"
+    raw = v.encode("utf-8")
+    out = bytearray(b"\x02")
+    n = len(raw) << 1  # zig-zag of a non-negative length
+    while n > 0x7F:
+        out.append((n & 0x7F) | 0x80)
+        n >>= 7
+    out.append(n)
+    return bytes(out) + raw
+
+
 @dataclass
 class SearchHit:
     document_id: str | None
@@ -41,6 +54,10 @@ class VectorTable:
         self.chunk: list[str | None] = []
         self.metadata: list[dict] = []
         self._row_of: dict[str, int] = {}
+        # the string columns pre-serialised as Avro ["null","string"] values (branch byte + length + utf-8): emitting a
+        # search_results record is then a concatenation of ready-made byte strings (pipeline/serve.py fast path)
+        self.avro_document_id: list[bytes] = []
+        self.avro_chunk: list[bytes] = []
 
     def __len__(self) -> int:
         return len(self.document_id)
@@ -64,8 +81,24 @@ class VectorTable:
             self.document_id.append(document_ids[i])
             self.chunk.append(chunks[i])
             self.metadata.append(metadata[i])
+            self.avro_document_id.append(_avro_nullable_string(document_ids[i]))
+            self.avro_chunk.append(_avro_nullable_string(chunks[i]))
             if document_ids[i] is not None:
                 self._row_of[document_ids[i]] = first + j
+
+    def load_columns(self, document_ids, chunks, metadata=None) -> None:
+        """Attach the non-vector columns for rows whose vectors are ALREADY in the index (bulk load of a pre-built
+        shard): row i of the index gets document_ids[i] / chunks[i]."""
+        assert len(self.document_id) == 0 and len(document_ids) == len(chunks)
+        metadata = metadata or [{} for _ in range(len(document_ids))]
+        for d, c, m in zip(document_ids, chunks, metadata):
+            if d is not None:
+                self._row_of[d] = len(self.document_id)
+            self.document_id.append(d)
+            self.chunk.append(c)
+            self.metadata.append(m)
+            self.avro_document_id.append(_avro_nullable_string(d))
+            self.avro_chunk.append(_avro_nullable_string(c))
 
     def clear(self) -> None:
         """What scripts/common/clear_mongodb.py:98-158 does before a re-publish."""
@@ -74,6 +107,8 @@ class VectorTable:
         self.chunk.clear()
         self.metadata.clear()
         self._row_of.clear()
+        self.avro_document_id.clear()
+        self.avro_chunk.clear()
 
 
 def vector_search_agg(table: VectorTable, descriptor: str, query_vectors: np.ndarray, k: int) -> list[list[SearchHit]]:
@@ -95,6 +130,22 @@ def vector_search_agg(table: VectorTable, descriptor: str, query_vectors: np.nda
             hits.append(SearchHit(table.document_id[i], table.chunk[i], float(s), int(i), table.metadata[i]))
         out.append(hits)
     return out
+
+
+def search_results_avro_body(table: VectorTable, query: str | None, score_row, idx_row, n: int = 3) -> bytes:
+    """Avro body of one ``search_results`` record straight from a result row (scores, table rows) -- byte-identical to
+    encoding ``flatten_search_results(...)`` with the generic codec, without building the dict."""
+    import struct
+    parts = [_avro_nullable_string(query)]
+    for j in range(n):
+        i = int(idx_row[j]) if j < len(idx_row) else -1
+        if i < 0:
+            parts.append(b"\x00\x00\x00")  # document_id, chunk, score all null
+        else:
+            parts.append(table.avro_document_id[i])
+            parts.append(table.avro_chunk[i])
+            parts.append(b"\x02" + struct.pack("<d", float(score_row[j])))
+    return b"".join(parts)
 
 
 def flatten_search_results(query: str | None, hits: list[SearchHit], n: int = 3) -> dict:

@@ -22,7 +22,7 @@ import time
 import numpy as np
 
 from ..embed.stub import StubEmbedder
-from ..operator import VectorTable, flatten_search_results, rag_prompt, vector_search_agg
+from ..operator import VectorTable, flatten_search_results, rag_prompt, search_results_avro_body, vector_search_agg
 from ..transport.filelog import Consumer, Producer
 from ..wire import avro, schemas
 from ..wire.registry import SchemaRegistry
@@ -61,6 +61,9 @@ class Codec:
             sid = self.registry.register(f"{topic}-value", schemas.TOPIC_SCHEMAS[topic])
             e = self._enc[topic] = (avro.frame(sid, b""), avro.CompiledSchema(schemas.TOPIC_SCHEMAS[topic]))
         return e
+
+    def header(self, topic: str) -> bytes:
+        return self._encoder(topic)[0]
 
     def encode(self, topic: str, record: dict) -> bytes:
         header, cs = self._encoder(topic)
@@ -170,26 +173,79 @@ class Lab2Pipeline:
             c.commit()
         return len(msgs)
 
-    def stage_search(self) -> int:
-        c, msgs, recs = self._drain("queries_embed")
-        texts, vecs = [], []
-        for m, r in recs:
-            vec = r.get("embedding")
-            if not self._check_vec("queries_embed", m, vec):
+    def _decode_queries_embed_fast(self, msgs):
+        """Batch decode of `queries_embed` records in their usual shape -- non-null query string, non-null single-block
+        array of dim non-null floats -- with one strided numpy gather for all embeddings.  Returns (texts, vectors,
+        leftovers): messages in any other shape are returned in `leftovers` for the generic per-record path."""
+        dim = self.table.index.dim
+        sid = self.codec.schema_id("queries_embed")
+        header = bytes([0]) + struct.pack(">I", sid)
+        block = bytearray()
+        avro.write_long(block, dim)
+        block = bytes(block)
+        span = 5 * dim
+        texts, views, leftovers = [], [], []
+        for m in msgs:
+            raw = m.value()
+            try:
+                if raw[:5] != header or raw[5] != 2:
+                    raise ValueError
+                n, pos = avro.read_long(raw, 6)
+                end = pos + n
+                if raw[end] != 2 or raw[end + 1:end + 1 + len(block)] != block:
+                    raise ValueError
+                off = end + 1 + len(block)
+                if len(raw) != off + span + 1 or raw[-1] != 0:
+                    raise ValueError
+                text = raw[pos:end].decode("utf-8")
+            except (ValueError, IndexError, TypeError):
+                leftovers.append(m)
                 continue
-            texts.append(r.get("query"))
-            vecs.append(vec)
-        if vecs:
+            texts.append(text)
+            views.append(np.frombuffer(raw, dtype=np.uint8, count=span, offset=off))
+        if not views:
+            return [], np.empty((0, dim), np.float32), leftovers
+        flat = np.stack(views).reshape(len(views), dim, 5)
+        ok = (flat[:, :, 0] == 2).all(axis=1)
+        vecs = np.ascontiguousarray(flat[:, :, 1:]).view("<f4").reshape(len(views), dim)
+        ok &= np.isfinite(vecs).all(axis=1)
+        if not ok.all():  # a null / non-finite item somewhere: let the generic path judge those records
+            bad = set(np.flatnonzero(~ok).tolist())
+            fast_msgs = [m for m in msgs if m not in leftovers]
+            leftovers.extend(fast_msgs[i] for i in sorted(bad))
+            keep = [i for i in range(len(views)) if i not in bad]
+            texts = [texts[i] for i in keep]
+            vecs = vecs[keep]
+        return texts, vecs, leftovers
+
+    def stage_search(self) -> int:
+        c = self.consumers["queries_embed"]
+        msgs = c.consume(self.max_batch, 0.0)
+        if not msgs:
+            return 0
+        texts, vecs, leftovers = self._decode_queries_embed_fast(msgs)
+        if leftovers:  # unusual layouts and poison records: generic codec, quarantine on failure
+            slow_t, slow_v = [], []
+            for m, r in self._decode_all("queries_embed", leftovers):
+                vec = r.get("embedding")
+                if self._check_vec("queries_embed", m, vec):
+                    slow_t.append(r.get("query"))
+                    slow_v.append(vec)
+            if slow_v:
+                texts = texts + slow_t
+                vecs = np.concatenate([vecs, np.stack(slow_v)]) if len(vecs) else np.stack(slow_v)
+        if len(texts):
             t0 = time.perf_counter()
-            hits = vector_search_agg(self.table, self.table.embedding_column, np.stack(vecs), self.k)
+            score, idx = self.table.index.search_host(np.ascontiguousarray(vecs, dtype=np.float32), self.k)
             self.stats["search_seconds"] += time.perf_counter() - t0
-            for q, h in zip(texts, hits):
-                self.producer.produce("search_results", value=self.codec.encode(
-                    "search_results", flatten_search_results(q, h, schemas.RESULTS_PER_QUERY)))
-            self.stats["searches"] += len(vecs)
-        if msgs:
-            self.producer.flush()
-            c.commit()
+            header = self.codec.header("search_results")
+            n_out = schemas.RESULTS_PER_QUERY
+            for r, q in enumerate(texts):
+                self.producer.produce("search_results",
+                                      value=header + search_results_avro_body(self.table, q, score[r], idx[r], n_out))
+            self.stats["searches"] += len(texts)
+        self.producer.flush()
+        c.commit()
         return len(msgs)
 
     def stage_response(self) -> int:

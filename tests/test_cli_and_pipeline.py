@@ -232,3 +232,46 @@ def test_pipeline_on_gpu(tmp_path):
         assert [table.document_id[j] for j in i[0]] == [r["document_id_1"], r["document_id_2"], r["document_id_3"]]
         assert abs(s[0, 0] - r["score_1"]) < 1e-6
     ix.close()
+
+
+def test_search_stage_fast_paths_equal_the_generic_codec(tmp_path):
+    """The search stage decodes `queries_embed` in batch and emits `search_results` from pre-serialised columns; both
+    shortcuts must be byte-for-byte what the generic codec produces, and odd-shaped records must fall back to it."""
+    import struct
+    from qsa_b200.operator import search_results_avro_body
+    logd = str(tmp_path / "topics")
+    idx = OracleIndex(64)
+    table = VectorTable(idx)
+    g = np.random.default_rng(0)
+    table.upsert_many([f"doc {i} é.md" for i in range(40)] + [None], [f"chunk {i} " * (i % 7) for i in range(40)] + [None],
+                      g.standard_normal((41, 64)).astype(np.float32))
+    pipe = Lab2Pipeline(logd, table, embedder=StubEmbedder(64), k=3)
+    codec = Codec(logd)
+    # (1) emit: concatenation of pre-serialised columns == generic encode of the flattened dict
+    q = g.standard_normal((5, 64)).astype(np.float32)
+    score, rows = idx.search_host(q, 3)
+    hits = vector_search_agg(table, "embedding", q, 3)
+    for r in range(5):
+        fast = search_results_avro_body(table, f"q{r}", score[r], rows[r], 3)
+        assert fast == avro.encode(schemas.SEARCH_RESULTS_VALUE, flatten_search_results(f"q{r}", hits[r], 3))
+    short = search_results_avro_body(table, None, score[0][:1], np.array([rows[0][0], -1, -1]), 3)
+    assert avro.decode(schemas.SEARCH_RESULTS_VALUE, short)["document_id_2"] is None
+    # (2) decode: usual shape goes through the batch path, unusual shapes through the generic one, same answers
+    p = Producer({"log.dir": logd})
+    vec = g.standard_normal(64).astype(np.float32)
+    p.produce("queries_embed", value=codec.encode("queries_embed", {"query": "usual", "embedding": vec}))
+    multi = bytearray(codec.header("queries_embed") + b"\x02" + bytes([2 * len("two blocks")]) + b"two blocks" + b"\x02")
+    for part in (vec[:10], vec[10:]):                       # the same vector as a two-block array
+        avro.write_long(multi, len(part))
+        for x in part:
+            multi += b"\x02" + struct.pack("<f", float(x))
+    multi += b"\x00"
+    p.produce("queries_embed", value=bytes(multi))
+    p.produce("queries_embed", value=codec.encode("queries_embed", {"query": None, "embedding": vec}))   # null query text
+    p.flush()
+    assert pipe.stage_search() == 3 and pipe.stats["quarantined"] == 0
+    c = Consumer({"log.dir": logd, "group.id": "t"}); c.subscribe(["search_results"])
+    out = [codec.decode(m.value()) for m in c.consume(10, 0.0)]
+    assert [o["query"] for o in out] == ["usual", "two blocks", None]
+    assert out[0]["document_id_1"] == out[1]["document_id_1"] == out[2]["document_id_1"]
+    assert out[0]["score_1"] == out[1]["score_1"]

@@ -23,7 +23,7 @@ if __name__ == "__main__":
     gpu = "--gpu" in sys.argv
     if gpu:
         sys.argv.remove("--gpu")
-    t = VectorTable(NullIndex()); t.document_id = [f"d{i}" for i in range(1000)]; t.chunk = ["chunk text " * 20] * 1000; t.metadata = [{}] * 1000
+    t = VectorTable(NullIndex()); t.load_columns([f"d{i}" for i in range(1000)], ["chunk text " * 20] * 1000)
     if gpu:   # the real engine over a 1M x 1536 corpus: QPS_e2e of the search stage over the file-log transport
         import torch
         from bench import fill_corpus
@@ -31,7 +31,7 @@ if __name__ == "__main__":
         rows = 1_000_000
         ix = VectorIndex(dim=1536, capacity=rows, max_batch=1024, max_k=3)
         fill_corpus(ix, rows, 1536, 7)
-        t = VectorTable(ix); t.document_id = [f"d{i}" for i in range(rows)]; t.chunk = ["chunk text " * 20] * rows; t.metadata = [{}] * rows
+        t = VectorTable(ix); t.load_columns([f"d{i}" for i in range(rows)], ["chunk text " * 20] * rows)
     pipe = Lab2Pipeline(d, t, k=3, max_batch=1024)
     codec = Codec(d); p = Producer({"log.dir": d})
     vec = np.random.randn(1536).astype(np.float32)
