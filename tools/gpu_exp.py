@@ -47,6 +47,9 @@ if __name__ == "__main__":
     fill_corpus(ix, rows, dim, 1234)
     g = torch.Generator(device="cuda").manual_seed(1)
     q = torch.randn((B, dim), generator=g, device="cuda").to(torch.bfloat16)
-    for cg, d, gain, mx in settings:
+    for st in settings:
+        cg, d, gain, mx = st[:4]
+        qpu2 = st[4] if len(st) > 4 else 1
         ix.set_option("cta_group", cg); ix.set_option("max_drift", d); ix.set_option("pace_gain", gain); ix.set_option("pace_max", mx)
-        run(ix, q, 10, iters, f"B={B} cg={cg} drift={d} gain={gain} max={mx}")
+        ix.set_option("qpu2", qpu2)
+        run(ix, q, 10, iters, f"B={B} cg={cg} drift={d} gain={gain} max={mx} qpu2={qpu2}")
