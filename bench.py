@@ -306,11 +306,34 @@ def run_b200(a):
     for _ in range(2):
         step_host()
     barrier()
-    t0 = time.perf_counter()
-    for _ in range(a.steps):
-        res_host = step_host()
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    if world == 1:
+        # As a serving loop drives it: the two host slots of the C ABI keep one batch on the device while the next is
+        # submitted.  Every step still moves its own queries host->device and its own results device->host inside the
+        # timed region; q_host2 / out_host2 alternate so no buffer is touched while in flight.
+        q_host2 = ix.pinned_array((B, dim), np.float32)
+        q_host2[:] = q_host
+        outs = (out_host, (ix.pinned_array((B, k), np.float32), ix.pinned_array((B, k), np.int32)))
+        qs = (q_host, q_host2)
+        t0 = time.perf_counter()
+        ix.search_host_submit(qs[0], k, 0)
+        for i in range(1, a.steps):
+            ix.search_host_submit(qs[i & 1], k, i & 1)
+            ix.search_host_wait((i - 1) & 1, out=outs[(i - 1) & 1])
+        res_host = ix.search_host_wait((a.steps - 1) & 1, out=outs[(a.steps - 1) & 1])
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        # the blocking call, one batch at a time (what a caller without pipelining sees)
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            res_host = step_host()
+        e2e_blocking_s = time.perf_counter() - t0
+    else:
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            res_host = step_host()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        e2e_blocking_s = e2e_s
     time.sleep(0.2)
     sampler.stop()
     clocks = sampler.summary(t_w0, time.perf_counter())   # timed loop + scan-event loop + e2e loop, all under load
@@ -364,7 +387,9 @@ def run_b200(a):
                        "l2": "inputs larger than L2 (corpus shard %.1f GB per step)" % (n_local * dim * 2 / 1e9),
                        "cta_group": a.cta_group or "auto"},
             "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": B * dim * 4, "d2h_bytes_per_step": B * k * (8 if world == 1 else 12),
-                    "api": "sa_search_host (C ABI, host fp32 queries in, host results out, page-locked buffers)" if world == 1 else
+                    "blocking_value": B * a.steps / e2e_blocking_s,
+                    "api": "sa_search_host_submit/_wait (C ABI, host fp32 queries in, host results out, page-locked buffers, "
+                           "2 batches in flight); blocking_value = sa_search_host one batch at a time" if world == 1 else
                            "ShardedIndex.search_host (H2D, shard scan, NCCL all-gather, merge, D2H)"},
             "gpu_launches": int(kernels_per_step * a.steps),
             "clocks": clocks, "roofline": roof,

@@ -37,6 +37,7 @@ typedef enum sa_status {
 } sa_status;
 
 #define SA_MAX_K 28 /* candidate lists hold k + 4 entries, at most 32 */
+#define SA_HOST_SLOTS 2 /* host-buffer searches that may be in flight at once (sa_search_host_submit) */
 
 int sa_version(void);
 const char* sa_strerror(int rc);
@@ -84,6 +85,13 @@ int sa_search_f32(sa_engine* e, const float* q_f32_dev, int nq, int k, float* ou
 /* End-to-end call with HOST buffers: H2D of the queries, search, D2H of the results; blocking. */
 int sa_search_host(sa_engine* e, const float* q_f32_host, int nq, int k, float* out_score_host,
                    int32_t* out_idx_host);
+
+/* The same call split in two, so a serving loop can decode / stage batch i+1 while the GPU works on batch i:
+ * submit enqueues H2D + search + D2H for `slot` (0 .. SA_HOST_SLOTS-1) and returns at once; wait blocks until that
+ * slot's results are in host memory and copies them out.  Searches execute in submission order.  A pageable query
+ * buffer may be reused as soon as submit returns; a page-locked one must stay unchanged until the matching wait. */
+int sa_search_host_submit(sa_engine* e, int slot, const float* q_f32_host, int nq, int k);
+int sa_search_host_wait(sa_engine* e, int slot, float* out_score_host, int32_t* out_idx_host);
 
 /* --- multi-GPU: after each rank searched its row shard and the per-rank (score64, global row) lists were
  *     all-gathered into [n_shards x nq x k] buffers, merge to the global top-k. --- */

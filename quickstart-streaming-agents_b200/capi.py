@@ -18,12 +18,13 @@ SA_ERR_COMM = -3
 SA_ERR_CAPACITY = -4
 SA_ERR_DEVICE = -5
 SA_MAX_K = 28
+SA_HOST_SLOTS = 2
 
 # every symbol include/sa_api.h declares (tests check the .so exports each of them)
 EXPORTS = (
     "sa_version", "sa_strerror", "sa_last_error", "sa_engine_create", "sa_engine_destroy", "sa_corpus_bind",
     "sa_corpus_commit", "sa_corpus_append_f32", "sa_corpus_append_host_f32", "sa_corpus_reset", "sa_corpus_rows",
-    "sa_search", "sa_search_f32", "sa_search_host", "sa_merge_shards", "sa_last_timing", "sa_timing_mean", "sa_set_option",
+    "sa_search", "sa_search_f32", "sa_search_host", "sa_search_host_submit", "sa_search_host_wait", "sa_merge_shards", "sa_last_timing", "sa_timing_mean", "sa_set_option",
     "sa_get_info", "sa_debug_tile_dots", "sa_debug_plan", "sa_host_alloc", "sa_host_free",
 )
 
@@ -67,6 +68,8 @@ def load() -> C.CDLL:
         "sa_search": (i32, [vp, vp, i32, i32, vp, vp, vp, vp]),
         "sa_search_f32": (i32, [vp, vp, i32, i32, vp, vp, vp, vp]),
         "sa_search_host": (i32, [vp, vp, i32, i32, vp, vp]),
+        "sa_search_host_submit": (i32, [vp, i32, vp, i32, i32]),
+        "sa_search_host_wait": (i32, [vp, i32, vp, vp]),
         "sa_merge_shards": (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp]),
         "sa_last_timing": (i32, [vp, f32p, f32p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i32),
                                  C.POINTER(i32)]),

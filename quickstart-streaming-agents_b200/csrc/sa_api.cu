@@ -67,6 +67,7 @@ int encode_rows_map(CUtensorMap* m, const void* base, uint64_t rows, int dim, in
 
 constexpr int kMaxLaunches = 16;
 constexpr int kTimingRing = 16;
+constexpr int kHostSlots = SA_HOST_SLOTS;
 
 }  // namespace
 
@@ -91,9 +92,16 @@ struct sa_engine {
   float* q_f32 = nullptr;       // [max_batch][dim]  (host-path staging on device)
   float* res_score = nullptr;   // [max_batch][max_k]
   int* res_idx = nullptr;
-  float* h_q = nullptr;         // pinned [max_batch][dim]
-  float* h_score = nullptr;     // pinned
-  int* h_idx = nullptr;         // pinned
+  // host-buffer path: pinned staging per slot (0,1 = public asynchronous slots, 2 = the blocking sa_search_host)
+  struct HostSlot {
+    float* h_q = nullptr;      // pinned [max_batch][dim]
+    float* h_score = nullptr;  // pinned [max_batch][max_k]
+    int* h_idx = nullptr;      // pinned
+    cudaEvent_t done = nullptr;
+    int nq = 0, k = 0;
+    bool busy = false;
+  };
+  HostSlot slot[kHostSlots + 1];
   float* d_stage = nullptr;     // device staging for host ingest
   float* h_stage = nullptr;     // pinned staging for host ingest
   int64_t stage_rows = 0;
@@ -431,9 +439,12 @@ int sa_engine_create(sa_engine** out, int device, int dim, int64_t capacity_rows
   SA_TRY(cudaMalloc(&e->res_score, relems * 4));
   SA_TRY(cudaMalloc(&e->res_idx, relems * 4));
   SA_TRY(cudaMalloc(&e->d_stage, static_cast<size_t>(e->stage_rows) * dim * 4));
-  SA_TRY(cudaHostAlloc(&e->h_q, qelems * 4, cudaHostAllocDefault));
-  SA_TRY(cudaHostAlloc(&e->h_score, relems * 4, cudaHostAllocDefault));
-  SA_TRY(cudaHostAlloc(&e->h_idx, relems * 4, cudaHostAllocDefault));
+  for (int i = 0; i <= kHostSlots; ++i) {
+    SA_TRY(cudaHostAlloc(&e->slot[i].h_q, qelems * 4, cudaHostAllocDefault));
+    SA_TRY(cudaHostAlloc(&e->slot[i].h_score, relems * 4, cudaHostAllocDefault));
+    SA_TRY(cudaHostAlloc(&e->slot[i].h_idx, relems * 4, cudaHostAllocDefault));
+    SA_TRY(cudaEventCreateWithFlags(&e->slot[i].done, cudaEventDisableTiming));
+  }
   SA_TRY(cudaHostAlloc(&e->h_stage, static_cast<size_t>(e->stage_rows) * dim * 4, cudaHostAllocDefault));
   // a blocking stream: ordered after work already queued on the legacy default stream (torch's default)
   SA_TRY(cudaStreamCreate(&e->own_stream));
@@ -466,9 +477,12 @@ void sa_engine_destroy(sa_engine* e) {
   cudaFree(e->res_score);
   cudaFree(e->res_idx);
   cudaFree(e->d_stage);
-  cudaFreeHost(e->h_q);
-  cudaFreeHost(e->h_score);
-  cudaFreeHost(e->h_idx);
+  for (int i = 0; i <= kHostSlots; ++i) {
+    cudaFreeHost(e->slot[i].h_q);
+    cudaFreeHost(e->slot[i].h_score);
+    cudaFreeHost(e->slot[i].h_idx);
+    if (e->slot[i].done) cudaEventDestroy(e->slot[i].done);
+  }
   cudaFreeHost(e->h_stage);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   cudaFree(e->lane_progress);
@@ -587,38 +601,75 @@ int sa_search_f32(sa_engine* e, const float* q_f32_dev, int nq, int k, float* ou
   return rc;
 }
 
-int sa_search_host(sa_engine* e, const float* q_f32_host, int nq, int k, float* out_score_host,
-                   int32_t* out_idx_host) {
-  int rc = check_engine(e);
-  if (rc) return rc;
-  if (!q_f32_host || !out_score_host || !out_idx_host) return fail(SA_ERR_ARG, "null buffer");
+namespace {
+
+int host_submit(sa_engine* e, int si, const float* q_f32_host, int nq, int k) {
+  sa_engine::HostSlot& sl = e->slot[si];
+  if (sl.busy) return fail(SA_ERR_ARG, "host slot %d still holds an unwaited search", si);
+  if (!q_f32_host) return fail(SA_ERR_ARG, "null buffer");
   if (nq <= 0 || nq > e->max_batch) return fail(SA_ERR_CAPACITY, "nq %d outside [1, max_batch %d]", nq, e->max_batch);
   if (k <= 0 || k > e->max_k) return fail(SA_ERR_ARG, "k %d outside [1, max_k %d]", k, e->max_k);
   SA_CUDA(cudaSetDevice(e->device));
   const size_t qbytes = static_cast<size_t>(nq) * e->dim * 4;
   const size_t rbytes = static_cast<size_t>(nq) * k * 4;
-  // Buffers that are already page-locked (sa_host_alloc, cudaHostRegister, torch pin_memory) are DMA'd directly;
-  // pageable ones go through the engine's pinned staging.
-  const bool q_pinned = is_pinned(q_f32_host);
-  const bool r_pinned = is_pinned(out_score_host) && is_pinned(out_idx_host);
+  // A query buffer that is already page-locked (sa_host_alloc, cudaHostRegister, torch pin_memory) is DMA'd
+  // directly -- the caller then keeps it unchanged until the matching wait; pageable memory is staged.
   const float* q_src = q_f32_host;
-  if (!q_pinned) {
-    memcpy(e->h_q, q_f32_host, qbytes);
-    q_src = e->h_q;
+  if (!is_pinned(q_f32_host)) {
+    memcpy(sl.h_q, q_f32_host, qbytes);
+    q_src = sl.h_q;
   }
   SA_CUDA(cudaMemcpyAsync(e->q_f32, q_src, qbytes, cudaMemcpyHostToDevice, e->own_stream));
-  rc = sa_search_f32(e, e->q_f32, nq, k, e->res_score, e->res_idx, nullptr, reinterpret_cast<uintptr_t>(e->own_stream));
+  int rc = sa_search_f32(e, e->q_f32, nq, k, e->res_score, e->res_idx, nullptr,
+                         reinterpret_cast<uintptr_t>(e->own_stream));
   if (rc) return rc;
-  float* s_dst = r_pinned ? out_score_host : e->h_score;
-  int32_t* i_dst = r_pinned ? out_idx_host : e->h_idx;
-  SA_CUDA(cudaMemcpyAsync(s_dst, e->res_score, rbytes, cudaMemcpyDeviceToHost, e->own_stream));
-  SA_CUDA(cudaMemcpyAsync(i_dst, e->res_idx, rbytes, cudaMemcpyDeviceToHost, e->own_stream));
-  SA_CUDA(cudaStreamSynchronize(e->own_stream));
-  if (!r_pinned) {
-    memcpy(out_score_host, e->h_score, rbytes);
-    memcpy(out_idx_host, e->h_idx, rbytes);
-  }
+  SA_CUDA(cudaMemcpyAsync(sl.h_score, e->res_score, rbytes, cudaMemcpyDeviceToHost, e->own_stream));
+  SA_CUDA(cudaMemcpyAsync(sl.h_idx, e->res_idx, rbytes, cudaMemcpyDeviceToHost, e->own_stream));
+  SA_CUDA(cudaEventRecord(sl.done, e->own_stream));
+  sl.nq = nq;
+  sl.k = k;
+  sl.busy = true;
   return SA_OK;
+}
+
+int host_wait(sa_engine* e, int si, float* out_score_host, int32_t* out_idx_host) {
+  sa_engine::HostSlot& sl = e->slot[si];
+  if (!sl.busy) return fail(SA_ERR_ARG, "host slot %d has no search in flight", si);
+  if (!out_score_host || !out_idx_host) return fail(SA_ERR_ARG, "null buffer");
+  SA_CUDA(cudaSetDevice(e->device));
+  SA_CUDA(cudaEventSynchronize(sl.done));
+  const size_t rbytes = static_cast<size_t>(sl.nq) * sl.k * 4;
+  memcpy(out_score_host, sl.h_score, rbytes);
+  memcpy(out_idx_host, sl.h_idx, rbytes);
+  sl.busy = false;
+  return SA_OK;
+}
+
+}  // namespace
+
+int sa_search_host(sa_engine* e, const float* q_f32_host, int nq, int k, float* out_score_host,
+                   int32_t* out_idx_host) {
+  int rc = check_engine(e);
+  if (rc) return rc;
+  if (!out_score_host || !out_idx_host) return fail(SA_ERR_ARG, "null buffer");
+  e->slot[kHostSlots].busy = false;  // the private slot of the blocking call
+  rc = host_submit(e, kHostSlots, q_f32_host, nq, k);
+  if (rc) return rc;
+  return host_wait(e, kHostSlots, out_score_host, out_idx_host);
+}
+
+int sa_search_host_submit(sa_engine* e, int slot, const float* q_f32_host, int nq, int k) {
+  int rc = check_engine(e);
+  if (rc) return rc;
+  if (slot < 0 || slot >= kHostSlots) return fail(SA_ERR_ARG, "slot %d outside [0, %d)", slot, kHostSlots);
+  return host_submit(e, slot, q_f32_host, nq, k);
+}
+
+int sa_search_host_wait(sa_engine* e, int slot, float* out_score_host, int32_t* out_idx_host) {
+  int rc = check_engine(e);
+  if (rc) return rc;
+  if (slot < 0 || slot >= kHostSlots) return fail(SA_ERR_ARG, "slot %d outside [0, %d)", slot, kHostSlots);
+  return host_wait(e, slot, out_score_host, out_idx_host);
 }
 
 int sa_merge_shards(sa_engine* e, const double* score64_dev, const int64_t* global_idx_dev, int n_shards, int nq,

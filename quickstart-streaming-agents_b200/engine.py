@@ -49,6 +49,7 @@ class VectorIndex:
                                              self.max_k), "sa_engine_create")
         self._h = h
         self._pinned = []
+        self._inflight = {}
         capi.check(self.lib.sa_corpus_bind(self._h, self.rows.data_ptr(), self.inv_norm.data_ptr(), 0),
                    "sa_corpus_bind")
 
@@ -167,6 +168,29 @@ class VectorIndex:
         torch.cuda.current_stream(self.device).synchronize()  # the *_host calls run on the engine's stream
         capi.check(self.lib.sa_search_host(self._h, q.ctypes.data, nq, k, score.ctypes.data, idx.ctypes.data),
                    "sa_search_host")
+        return score, idx
+
+    def search_host_submit(self, q_f32: np.ndarray, k: int, slot: int = 0) -> None:
+        """First half of ``search_host``: enqueue H2D + search + D2H for ``slot`` (0 or 1) and return at once, so the
+        caller can prepare the next batch while the GPU works.  Collect with ``search_host_wait(slot)``."""
+        q = np.ascontiguousarray(q_f32, dtype=np.float32)
+        assert q.ndim == 2 and q.shape[1] == self.dim
+        torch.cuda.current_stream(self.device).synchronize()  # the *_host calls run on the engine's own stream
+        self._inflight[slot] = (q, q.shape[0], k)  # keeps a pinned source alive until the wait
+        capi.check(self.lib.sa_search_host_submit(self._h, slot, q.ctypes.data, q.shape[0], k),
+                   "sa_search_host_submit")
+
+    def search_host_wait(self, slot: int = 0, out=None):
+        _, nq, k = self._inflight.pop(slot)
+        if out is None:
+            score = np.empty((nq, k), dtype=np.float32)
+            idx = np.empty((nq, k), dtype=np.int32)
+        else:
+            score, idx = out
+            assert score.shape == (nq, k) and score.dtype == np.float32 and score.flags.c_contiguous
+            assert idx.shape == (nq, k) and idx.dtype == np.int32 and idx.flags.c_contiguous
+        capi.check(self.lib.sa_search_host_wait(self._h, slot, score.ctypes.data, idx.ctypes.data),
+                   "sa_search_host_wait")
         return score, idx
 
     def pinned_array(self, shape, dtype=np.float32) -> np.ndarray:

@@ -218,13 +218,10 @@ class Lab2Pipeline:
             vecs = vecs[keep]
         return texts, vecs, leftovers
 
-    def stage_search(self) -> int:
-        c = self.consumers["queries_embed"]
-        msgs = c.consume(self.max_batch, 0.0)
-        if not msgs:
-            return 0
+    def _decode_batch(self, msgs):
+        """queries_embed messages -> (texts, vectors): fast batch path, generic codec (and quarantine) for the rest."""
         texts, vecs, leftovers = self._decode_queries_embed_fast(msgs)
-        if leftovers:  # unusual layouts and poison records: generic codec, quarantine on failure
+        if leftovers:
             slow_t, slow_v = [], []
             for m, r in self._decode_all("queries_embed", leftovers):
                 vec = r.get("embedding")
@@ -234,19 +231,61 @@ class Lab2Pipeline:
             if slow_v:
                 texts = texts + slow_t
                 vecs = np.concatenate([vecs, np.stack(slow_v)]) if len(vecs) else np.stack(slow_v)
-        if len(texts):
-            t0 = time.perf_counter()
-            score, idx = self.table.index.search_host(np.ascontiguousarray(vecs, dtype=np.float32), self.k)
-            self.stats["search_seconds"] += time.perf_counter() - t0
-            header = self.codec.header("search_results")
-            n_out = schemas.RESULTS_PER_QUERY
-            for r, q in enumerate(texts):
-                self.producer.produce("search_results",
-                                      value=header + search_results_avro_body(self.table, q, score[r], idx[r], n_out))
-            self.stats["searches"] += len(texts)
-        self.producer.flush()
-        c.commit()
-        return len(msgs)
+        return texts, np.ascontiguousarray(vecs, dtype=np.float32)
+
+    def _emit_results(self, texts, score, idx) -> None:
+        header = self.codec.header("search_results")
+        n_out = schemas.RESULTS_PER_QUERY
+        for r, q in enumerate(texts):
+            self.producer.produce("search_results",
+                                  value=header + search_results_avro_body(self.table, q, score[r], idx[r], n_out))
+        self.stats["searches"] += len(texts)
+
+    def stage_search(self) -> int:
+        """queries_embed -> VECTOR_SEARCH_AGG -> search_results.  When the index offers the split host call
+        (``search_host_submit`` / ``search_host_wait``), batches are software-pipelined: batch i+1 is read and decoded
+        while the GPU searches batch i.  Offsets of a batch are committed only after its results are flushed."""
+        c = self.consumers["queries_embed"]
+        index = self.table.index
+        pipelined = hasattr(index, "search_host_submit")
+        total = 0
+        pending = None  # (messages, texts, slot) of the batch the GPU is working on
+        slot = 0
+        while True:
+            msgs = c.consume(self.max_batch, 0.0)
+            batch = None
+            if msgs:
+                total += len(msgs)
+                texts, vecs = self._decode_batch(msgs)
+                batch = (msgs, texts, vecs)
+            if batch is not None and len(batch[1]) and pipelined:
+                t0 = time.perf_counter()
+                index.search_host_submit(batch[2], self.k, slot)
+                self.stats["search_seconds"] += time.perf_counter() - t0
+            if pending is not None:  # collect the previous batch while the new one runs
+                p_msgs, p_texts, p_slot = pending
+                t0 = time.perf_counter()
+                score, idx = index.search_host_wait(p_slot)
+                self.stats["search_seconds"] += time.perf_counter() - t0
+                self._emit_results(p_texts, score, idx)
+                self.producer.flush()
+                c.commit_offsets(p_msgs)
+                pending = None
+            if batch is None:
+                break
+            msgs, texts, vecs = batch
+            if len(texts) and pipelined:
+                pending = (msgs, texts, slot)
+                slot ^= 1
+            else:
+                if len(texts):
+                    t0 = time.perf_counter()
+                    score, idx = index.search_host(vecs, self.k)
+                    self.stats["search_seconds"] += time.perf_counter() - t0
+                    self._emit_results(texts, score, idx)
+                self.producer.flush()  # also carries any quarantined records of this batch
+                c.commit_offsets(msgs)
+        return total
 
     def stage_response(self) -> int:
         c, msgs, recs = self._drain("search_results")

@@ -315,6 +315,16 @@ class Consumer:
         else:
             self.broker.commit(self.group, {f"{t}-{p}": o for (t, p), o in self._pos.items()})
 
+    def commit_offsets(self, messages) -> None:
+        """Commit exactly up to (and including) the given messages -- for pipelined stages that have consumed further
+        ahead than they have finished processing."""
+        offs: dict[str, int] = {}
+        for m in messages:
+            key = f"{m.topic()}-{m.partition()}"
+            offs[key] = max(offs.get(key, 0), m.offset() + 1)
+        if offs:
+            self.broker.commit(self.group, offs)
+
     def position(self, tp: TopicPartition) -> int:
         return self._pos.get((tp.topic, tp.partition), -1)
 

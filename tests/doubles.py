@@ -41,3 +41,20 @@ class OracleIndex:
         s, i = bf.merge_shard_topk([all_s[j].numpy() for j in range(g)], [all_i[j].numpy() for j in range(g)],
                                    [0] * g, all_s.shape[2])
         return torch.from_numpy(s.astype(np.float32)), torch.from_numpy(i)
+
+
+class PipelinedOracleIndex(OracleIndex):
+    """Adds the split host call (submit / wait) so the serve loop's software pipelining runs on a CPU box."""
+
+    def __init__(self, dim, capacity=1 << 20):
+        super().__init__(dim, capacity)
+        self._slots = {}
+        self.max_inflight = 0
+
+    def search_host_submit(self, q_f32, k, slot=0):
+        assert slot not in self._slots, "slot reused before wait"
+        self._slots[slot] = self.search_host(q_f32, k)
+        self.max_inflight = max(self.max_inflight, len(self._slots))
+
+    def search_host_wait(self, slot=0, out=None):
+        return self._slots.pop(slot)

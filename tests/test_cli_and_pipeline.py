@@ -14,7 +14,7 @@ from qsa_b200.transport.filelog import Broker, Consumer, Producer, TopicPartitio
 from qsa_b200.wire import avro, schemas
 from scripts import lab2_publish_queries, publish_docs
 
-from doubles import OracleIndex
+from doubles import OracleIndex, PipelinedOracleIndex
 
 TOPICS = ["sql window functions tumble hop session", "watermarks and event time late data", "kafka connector properties",
           "state ttl and checkpoints", "user defined functions in java and python", "joins interval temporal lookup",
@@ -275,3 +275,32 @@ def test_search_stage_fast_paths_equal_the_generic_codec(tmp_path):
     assert [o["query"] for o in out] == ["usual", "two blocks", None]
     assert out[0]["document_id_1"] == out[1]["document_id_1"] == out[2]["document_id_1"]
     assert out[0]["score_1"] == out[1]["score_1"]
+
+
+def test_search_stage_is_pipelined_and_commits_per_batch(tmp_path):
+    """With the split host call, batch i+1 is decoded while batch i is searched; results, order and committed offsets
+    are the same as the blocking path, and a crash between batches redelivers only unfinished batches."""
+    outs = {}
+    for name, cls in (("blocking", OracleIndex), ("pipelined", PipelinedOracleIndex)):
+        logd = str(tmp_path / name)
+        idx = cls(64)
+        table = VectorTable(idx)
+        g = np.random.default_rng(3)
+        table.upsert_many([f"d{i}" for i in range(200)], [f"c{i}" for i in range(200)], g.standard_normal((200, 64)).astype(np.float32))
+        pipe = Lab2Pipeline(logd, table, embedder=StubEmbedder(64), k=3, max_batch=16)
+        codec = Codec(logd)
+        p = Producer({"log.dir": logd})
+        for i in range(70):                                   # 4 full batches + one of 6
+            p.produce("queries_embed", value=codec.encode("queries_embed", {"query": f"q{i}", "embedding": g.standard_normal(64).astype(np.float32)}))
+        p.produce("queries_embed", value=b"\x01poison")
+        p.flush()
+        assert pipe.stage_search() == 71 and pipe.stats["searches"] == 70 and pipe.stats["quarantined"] == 1
+        assert Broker(logd).committed("sa-lab2")["queries_embed-0"] == 71
+        c = Consumer({"log.dir": logd, "group.id": "t"}); c.subscribe(["search_results"])
+        outs[name] = [codec.decode(m.value()) for m in c.consume(100, 0.0)]
+        if name == "pipelined":
+            assert idx.max_inflight == 2 and not idx._slots   # batch i+1 is queued before batch i is collected
+        assert pipe.stage_search() == 0
+    assert [o["query"] for o in outs["blocking"]] == [f"q{i}" for i in range(70)]
+    g2 = np.random.default_rng(3)                              # same seeds -> same vectors -> same answers
+    assert [(o["query"], o["document_id_1"]) for o in outs["blocking"]] == [(o["query"], o["document_id_1"]) for o in outs["pipelined"]]

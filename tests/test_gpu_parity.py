@@ -389,3 +389,42 @@ def test_near_duplicate_cluster_does_not_break_exactness(bf, cg):
     assert set(i[0]).issubset(set(crowd.tolist()) | {123})
     check(ix, q, c, 20, cg)                                  # 32-entry lists, 64-wide rescoring
     ix.close()
+
+
+def test_host_slots_submit_wait(bf):
+    """sa_search_host_submit / _wait: two batches in flight, results come back per slot in submission order, misuse
+    is an error, and the blocking call still works in between."""
+    from qsa_b200 import capi
+    from qsa_b200.engine import VectorIndex
+    dim, n, k = 256, 20000, 10
+    c = bf.synth_rows(81, 0, n, dim)
+    ix = VectorIndex(dim=dim, capacity=n, max_batch=300, max_k=10)
+    ix.append_bf16_bits(c)
+    batches = [bf.synth_queries(90 + j, nq, dim, c) for j, nq in enumerate((300, 17, 128, 256, 1))]
+    refs = [bf.cosine_topk_f64(q, c, k) for q in batches]
+    f32 = [bf.bf16_bits_to_f32(q) for q in batches]
+    pinned = ix.pinned_array((300, dim), np.float32)
+    got = {}
+    ix.search_host_submit(f32[0], k, 0)
+    for j in range(1, len(batches)):
+        src = f32[j]
+        if j == 2:                                   # a page-locked source is DMA'd in place
+            pinned[:len(src)] = src
+            src = pinned[:len(src)]
+        ix.search_host_submit(src, k, j & 1)
+        got[j - 1] = ix.search_host_wait((j - 1) & 1)
+    got[len(batches) - 1] = ix.search_host_wait((len(batches) - 1) & 1)
+    for j, (rs, ri) in enumerate(refs):
+        assert (got[j][1] == ri).all() and np.abs(got[j][0].astype(np.float64) - rs).max() < SCORE_TOL
+    ix.search_host_submit(f32[1], k, 0)
+    with pytest.raises(capi.SaError, match="unwaited"):
+        ix.lib and capi.check(ix.lib.sa_search_host_submit(ix._h, 0, f32[1].ctypes.data, 17, k), "submit")
+    hs, hi = ix.search_host(f32[2], k)               # the blocking call has its own slot
+    assert (hi == refs[2][1]).all()
+    s0, i0 = ix.search_host_wait(0)
+    assert (i0 == refs[1][1]).all()
+    with pytest.raises(capi.SaError, match="no search in flight"):
+        capi.check(ix.lib.sa_search_host_wait(ix._h, 1, hs.ctypes.data, hi.ctypes.data), "wait")
+    with pytest.raises(capi.SaError):
+        capi.check(ix.lib.sa_search_host_submit(ix._h, 2, f32[1].ctypes.data, 17, k), "submit")
+    ix.close()
