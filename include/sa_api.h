@@ -110,7 +110,7 @@ int sa_last_timing(sa_engine* e, float* scan_ms, float* total_ms, double* bytes,
 int sa_timing_mean(sa_engine* e, int n, float* scan_ms_mean, float* total_ms_mean, int* n_used);
 /* Options: "cta_group" = 0 (auto) | 1 | 2;  "max_launch_qblocks" = cap on query blocks per scan launch;
  * drift control between query blocks that share corpus tiles (keeps a shared tile L2-resident so it crosses HBM
- * once): "max_drift" = unpaced lead in tiles (default 1), "pace_gain" = delay cycles per K-slice per extra tile
+ * once): "max_drift" = unpaced lead in tiles (-1 auto), "pace_gain" = delay cycles per K-slice per extra tile
  * of lead (-1 auto, 0 off), "pace_max" = cap of that delay (-1 auto);
  * "qpu2" = 1 | 0 (let a unit carry two query blocks when that fills more SMs; default 1),
  * "share_thresholds" = 1 | 0 (tile lanes exchange per-query top-k thresholds; default 1), "list_len" = 0 (auto) | 16 | 32,

@@ -117,7 +117,7 @@ struct sa_engine {
   // options
   int opt_cta_group = 0;
   int opt_max_launch_qblocks = 0;
-  int opt_max_drift = 1;
+  int opt_max_drift = -1;  // -1 = auto (1 tile; 0 with two passes per tile)
   int opt_pace_gain = -1;  // -1 = auto (16 cycles/tile for CTA pairs, 32 for single CTAs), 0 = off
   int opt_pace_max = -1;   // -1 = auto (8 x gain)
   int opt_unit_map = 0;
@@ -312,12 +312,16 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
     sp.part_idx = e->part_idx;
     sp.corpus_evict_first = (lp.nqb == 1) ? 1 : 0;  // a tile nobody else will ask for: stream it through L2
     sp.lane_progress = nullptr;
-    sp.max_drift = e->opt_max_drift;
+    sp.max_drift = std::max(e->opt_max_drift, 0);
     sp.pace_gain = 0;
     sp.pace_max = e->opt_pace_max;
     sp.unit_map = e->opt_unit_map;
-    const int gain = e->opt_pace_gain >= 0 ? e->opt_pace_gain : (lp.cg == 2 ? 16 : 32);
+    // drift-control defaults from the sweeps in tools/gpu_l2exp.sh (DRAM bytes vs time): pairs 16 cycles per tile of
+    // lead beyond 1 tile, single CTAs 32; with two passes per tile (qpu 2) a tile of lead is twice as long, so pace
+    // from the first tile of lead and twice as hard
+    const int gain = e->opt_pace_gain >= 0 ? e->opt_pace_gain : ((lp.cg == 2 && lp.qpu == 1) ? 16 : 32);
     sp.pace_max = e->opt_pace_max >= 0 ? e->opt_pace_max : 8 * gain;
+    if (e->opt_max_drift < 0) sp.max_drift = lp.qpu == 2 ? 0 : 1;
     const int nslots = (lp.nqb + lp.qpu - 1) / lp.qpu;  // units per tile lane
     if (nslots > 1 && gain > 0) {
       sp.lane_progress = e->lane_progress;
@@ -790,7 +794,7 @@ int sa_set_option(sa_engine* e, const char* name, int64_t value) {
     return SA_OK;
   }
   if (!strcmp(name, "max_drift")) {
-    if (value < 0 || value > 1024) return fail(SA_ERR_ARG, "max_drift must be in [0, 1024]");
+    if (value < -1 || value > 1024) return fail(SA_ERR_ARG, "max_drift must be in [-1, 1024]");
     e->opt_max_drift = static_cast<int>(value);
     return SA_OK;
   }
