@@ -112,7 +112,7 @@ int sa_timing_mean(sa_engine* e, int n, float* scan_ms_mean, float* total_ms_mea
  * drift control between query blocks that share corpus tiles (keeps a shared tile L2-resident so it crosses HBM
  * once): "max_drift" = unpaced lead in tiles (-1 auto), "pace_gain" = delay cycles per K-slice per extra tile
  * of lead (-1 auto, 0 off), "pace_max" = cap of that delay (-1 auto);
- * "qpu2" = 1 | 0 (let a unit carry two query blocks when that fills more SMs; default 1),
+ * "qpu2" = 0 (default) | 1 (when it fills more SMs) | 2 (always): let a unit carry two query blocks,
  * "share_thresholds" = 1 | 0 (tile lanes exchange per-query top-k thresholds; default 1), "list_len" = 0 (auto) | 16 | 32,
  * "unit_map" = 0 | 1 (CTA -> (query block, tile lane) mapping), "record_times" = 0 | 1 (per-CTA timestamps). */
 int sa_set_option(sa_engine* e, const char* name, int64_t value);

@@ -121,7 +121,9 @@ struct sa_engine {
   int opt_pace_gain = -1;  // -1 = auto (16 cycles/tile for CTA pairs, 32 for single CTAs), 0 = off
   int opt_pace_max = -1;   // -1 = auto (8 x gain)
   int opt_unit_map = 0;
-  int opt_qpu2 = 1;       // allow two query blocks per unit when that fills more SMs
+  int opt_qpu2 = 0;       // 0 never (default), 1 when it shortens the tile walk, 2 always: two query blocks per unit.
+                          // Off by default: measured neutral under the power cap, and with two passes per tile a
+                          // lane-mate arrives later, so the shared tile is less reliably still in L2 (DRAM 1.07-1.4x)
   int opt_list_len = 0;   // 0 = auto (16 when k <= 12, else 32)
 
   // timing: CUDA events of the most recent kTimingRing searches

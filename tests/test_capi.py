@@ -67,7 +67,7 @@ def test_missing_library_raises(monkeypatch, tmp_path):
         capi.load()
 
 
-def plan(lib, num_sms, nq, cg, num_tiles, cap=0, qpu2=1):
+def plan(lib, num_sms, nq, cg, num_tiles, cap=0, qpu2=0):
     out = (C.c_int * (5 * 16))()
     n = C.c_int()
     rc = lib.sa_debug_plan(num_sms, nq, cg, num_tiles, cap, qpu2, out, 16, C.byref(n))
@@ -99,10 +99,10 @@ def test_launch_planner_invariants(lib, cg, qpu2, nq, num_tiles):
 
 
 def test_launch_planner_headline_shapes(lib):
-    assert plan(lib, 148, 1024, 2, 39063) == [(0, 1024, 4, 37, 2)]           # 2 slots x 37 lanes = all 74 pairs
-    assert plan(lib, 148, 1024, 2, 39063, qpu2=0) == [(0, 1024, 4, 18, 1)]   # 4 pair blocks x 18 lanes = 72 pairs
+    assert plan(lib, 148, 1024, 2, 39063) == [(0, 1024, 4, 18, 1)]           # 4 pair blocks x 18 lanes = 72 pairs
+    assert plan(lib, 148, 1024, 2, 39063, qpu2=1) == [(0, 1024, 4, 37, 2)]   # 2 slots x 37 lanes = all 74 pairs
     assert plan(lib, 148, 128, 1, 39063) == [(0, 128, 1, 148, 1)]            # HBM-bound: every SM its own lane
     assert plan(lib, 148, 512, 2, 39063) == [(0, 512, 2, 37, 1)]             # already fills the machine
-    p = plan(lib, 148, 4096, 2, 4883, qpu2=0)                                # config 4 per GPU: 2 launches of 8 x 9
+    p = plan(lib, 148, 4096, 2, 4883)                                        # config 4 per GPU: 2 launches of 8 x 9
     assert [x[2:] for x in p] == [(8, 9, 1), (8, 9, 1)]
     assert len(plan(lib, 148, 1100, 2, 118, cap=2)) == 3                     # forced small launches
