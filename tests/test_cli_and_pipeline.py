@@ -304,3 +304,20 @@ def test_search_stage_is_pipelined_and_commits_per_batch(tmp_path):
     assert [o["query"] for o in outs["blocking"]] == [f"q{i}" for i in range(70)]
     g2 = np.random.default_rng(3)                              # same seeds -> same vectors -> same answers
     assert [(o["query"], o["document_id_1"]) for o in outs["blocking"]] == [(o["query"], o["document_id_1"]) for o in outs["pipelined"]]
+
+
+@pytest.mark.gpu
+def test_sa_serve_cli_once_on_gpu(tmp_path, capsys):
+    """The serve CLI end to end: publish with the drop-in CLIs, `sa_serve --once`, read the result topics."""
+    from scripts import sa_serve
+    docs, logd = tmp_path / "docs", str(tmp_path / "topics")
+    write_docs(docs, 40)
+    assert publish_docs.main(["--docs-dir", str(docs), "--log-dir", logd]) == 0
+    assert lab2_publish_queries.main(["How do tumble windows work?", "--log-dir", logd]) == 0
+    capsys.readouterr()
+    assert sa_serve.main(["--log-dir", logd, "--once", "--capacity", "1024", "--max-batch", "64", "--k", "3"]) == 0
+    stats = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert stats["documents"] == 41 and stats["searches"] == 1 and stats["responses"] == 1 and stats["quarantined"] == 0
+    c = Consumer({"log.dir": logd, "group.id": "t"}); c.subscribe(["search_results_response"])
+    row = Codec(logd).decode(c.consume(1, 0.0)[0].value())
+    assert row["query"] == "How do tumble windows work?" and row["response"] and "window functions" in row["chunk_1"].lower()
