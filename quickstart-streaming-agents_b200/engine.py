@@ -118,6 +118,33 @@ class VectorIndex:
         self.commit(first, n)
         return first
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    def snapshot(self, path: str) -> int:
+        """Write the committed rows (bf16 bits) and their inverse norms to ``path`` (.npz).  Returns the row count.
+        (The reference leaves corpus durability to Atlas; here a snapshot + the consumer-group offsets are the
+        checkpoint, and replaying `documents_embed` from offset 0 is the fallback.)"""
+        n = len(self)
+        torch.cuda.current_stream(self.device).synchronize()
+        bits = self.rows[:n].view(torch.int16).cpu().numpy().view(np.uint16)
+        np.savez(path, rows=bits, inv_norm=self.inv_norm[:n].cpu().numpy(), dim=np.int64(self.dim))
+        return n
+
+    def restore(self, path: str) -> int:
+        """Load a snapshot written by ``snapshot`` into this (empty or not) index, replacing its contents."""
+        z = np.load(path if path.endswith(".npz") else path + ".npz")
+        if int(z["dim"]) != self.dim:
+            raise ValueError(f"snapshot has dim {int(z['dim'])}, index has {self.dim}")
+        bits, inv = z["rows"], z["inv_norm"]
+        n = bits.shape[0]
+        if n > self.capacity:
+            raise capi.SaError(capi.SA_ERR_CAPACITY, "restore", "snapshot larger than capacity")
+        self.rows[:n].copy_(torch.from_numpy(bits.view(np.int16)).view(torch.bfloat16))
+        self.inv_norm[:n].copy_(torch.from_numpy(inv))
+        torch.cuda.current_stream(self.device).synchronize()
+        capi.check(self.lib.sa_corpus_bind(self._h, self.rows.data_ptr(), self.inv_norm.data_ptr(), n),
+                   "sa_corpus_bind")
+        return n
+
     def delete_rows(self, rows) -> None:
         """Tombstone rows: zero the stored vector and its inverse norm -- all-zero rows are never returned."""
         if len(rows) == 0:

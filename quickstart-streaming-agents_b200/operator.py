@@ -100,6 +100,37 @@ class VectorTable:
             self.avro_document_id.append(_avro_nullable_string(d))
             self.avro_chunk.append(_avro_nullable_string(c))
 
+    def save(self, directory: str) -> int:
+        """Checkpoint: the index snapshot (if the index supports it) + the side table as JSON lines."""
+        import json
+        import os
+        os.makedirs(directory, exist_ok=True)
+        if hasattr(self.index, "snapshot"):
+            self.index.snapshot(os.path.join(directory, "index.npz"))
+        tmp = os.path.join(directory, "columns.jsonl.tmp")
+        with open(tmp, "w", encoding="utf-8") as f:
+            for d, c, m in zip(self.document_id, self.chunk, self.metadata):
+                f.write(json.dumps({"document_id": d, "chunk": c, "metadata": m}, ensure_ascii=False) + "\n")
+        os.replace(tmp, os.path.join(directory, "columns.jsonl"))
+        return len(self)
+
+    def load(self, directory: str) -> int:
+        """Resume from ``save``: restores the index and the side table (must be called on an empty table)."""
+        import json
+        import os
+        assert len(self) == 0, "load() needs an empty table"
+        rows = []
+        with open(os.path.join(directory, "columns.jsonl"), encoding="utf-8") as f:
+            for line in f:
+                rows.append(json.loads(line))
+        if hasattr(self.index, "restore"):
+            n = self.index.restore(os.path.join(directory, "index.npz"))
+            if n != len(rows):
+                raise ValueError(f"snapshot mismatch: {n} vectors, {len(rows)} column rows")
+        self.load_columns([r["document_id"] for r in rows], [r["chunk"] for r in rows], [r["metadata"] for r in rows])
+        # a re-published document tombstones its old row: the live row of an id is its LAST occurrence
+        return len(self)
+
     def clear(self) -> None:
         """What scripts/common/clear_mongodb.py:98-158 does before a re-publish."""
         self.index.reset()
@@ -111,8 +142,18 @@ class VectorTable:
         self.avro_chunk.clear()
 
 
-def vector_search_agg(table: VectorTable, descriptor: str, query_vectors: np.ndarray, k: int) -> list[list[SearchHit]]:
-    """VECTOR_SEARCH_AGG(table, DESCRIPTOR(descriptor), query_vector, k) for a batch of query vectors."""
+def atlas_score(cosine: float) -> float:
+    """MongoDB Atlas reports cosine similarity normalised to [0, 1] as (1 + cos) / 2; the engine's native score is the
+    raw cosine (what BASELINE.json's numpy yardstick uses).  Apply this where a downstream consumer expects Atlas's."""
+    return 0.5 * (1.0 + cosine)
+
+
+def vector_search_agg(table: VectorTable, descriptor: str, query_vectors: np.ndarray, k: int,
+                      score_mode: str = "cosine") -> list[list[SearchHit]]:
+    """VECTOR_SEARCH_AGG(table, DESCRIPTOR(descriptor), query_vector, k) for a batch of query vectors.
+    ``score_mode``: "cosine" (raw, default) or "atlas" ((1 + cos) / 2)."""
+    if score_mode not in ("cosine", "atlas"):
+        raise ValueError("score_mode must be 'cosine' or 'atlas'")
     if descriptor != table.embedding_column:
         raise ValueError(f"table {table.name} has no vector column {descriptor!r}")
     q = np.ascontiguousarray(query_vectors, dtype=np.float32)
@@ -127,6 +168,7 @@ def vector_search_agg(table: VectorTable, descriptor: str, query_vectors: np.nda
         for s, i in zip(score[r].tolist(), idx[r].tolist()):
             if i < 0:
                 break
+            s = atlas_score(s) if score_mode == "atlas" else s
             hits.append(SearchHit(table.document_id[i], table.chunk[i], float(s), int(i), table.metadata[i]))
         out.append(hits)
     return out

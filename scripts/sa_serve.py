@@ -28,6 +28,9 @@ def main(argv=None) -> int:
     ap.add_argument("--max-batch", type=int, default=1024)
     ap.add_argument("--k", type=int, default=3, help="VECTOR_SEARCH_AGG k (the reference uses 3)")
     ap.add_argument("--once", action="store_true", help="process everything pending, print stats, exit")
+    ap.add_argument("--snapshot-dir", default=None,
+                    help="checkpoint directory: loaded at start if present, written on exit (with the consumer-group "
+                         "offsets in the log directory this makes the loop resumable without replaying `documents`)")
     ap.add_argument("--verbose", action="store_true")
     a = ap.parse_args(argv)
     setup_logging(a.verbose)
@@ -37,7 +40,11 @@ def main(argv=None) -> int:
     from qsa_b200.pipeline.serve import Lab2Pipeline
 
     index = VectorIndex(dim=a.dim, capacity=a.capacity, max_batch=a.max_batch, max_k=max(a.k, 3))
-    pipe = Lab2Pipeline(resolve_log_dir(a.log_dir), VectorTable(index), k=a.k, max_batch=a.max_batch)
+    import os
+    table = VectorTable(index)
+    if a.snapshot_dir and os.path.exists(os.path.join(a.snapshot_dir, "columns.jsonl")):
+        print(f"resumed {table.load(a.snapshot_dir)} rows from {a.snapshot_dir}", file=sys.stderr)
+    pipe = Lab2Pipeline(resolve_log_dir(a.log_dir), table, k=a.k, max_batch=a.max_batch)
     try:
         if a.once:
             pipe.run_until_idle()
@@ -46,6 +53,9 @@ def main(argv=None) -> int:
             pipe.run_forever()
     except KeyboardInterrupt:
         print(json.dumps(pipe.stats))
+    finally:
+        if a.snapshot_dir:
+            table.save(a.snapshot_dir)
     return 0
 
 

@@ -321,3 +321,40 @@ def test_sa_serve_cli_once_on_gpu(tmp_path, capsys):
     c = Consumer({"log.dir": logd, "group.id": "t"}); c.subscribe(["search_results_response"])
     row = Codec(logd).decode(c.consume(1, 0.0)[0].value())
     assert row["query"] == "How do tumble windows work?" and row["response"] and "window functions" in row["chunk_1"].lower()
+
+
+def test_table_checkpoint_resume_and_atlas_score(tmp_path):
+    """Checkpoint / resume of the vector table (side columns here; the HBM half is covered on the GPU), tombstones
+    survive, and the optional Atlas score normalisation."""
+    from qsa_b200.operator import atlas_score
+
+    class SnapIndex(OracleIndex):
+        def snapshot(self, path):
+            np.savez(path, rows=self.bits)
+            return len(self.bits)
+
+        def restore(self, path):
+            self.bits = np.load(path)["rows"]
+            return len(self.bits)
+
+    g = np.random.default_rng(5)
+    t = VectorTable(SnapIndex(64))
+    vecs = g.standard_normal((30, 64)).astype(np.float32)
+    t.upsert_many([f"d{i}" for i in range(30)], [f"c{i} é" for i in range(30)], vecs, [{"pages": str(i)} for i in range(30)])
+    t.upsert_many(["d7"], ["c7 new"], g.standard_normal((1, 64)).astype(np.float32), [{"pages": "x"}])   # tombstones row 7
+    assert t.save(str(tmp_path / "ckpt")) == 31
+    t2 = VectorTable(SnapIndex(64))
+    assert t2.load(str(tmp_path / "ckpt")) == 31
+    assert t2.document_id == t.document_id and t2.chunk == t.chunk and t2.metadata == t.metadata
+    assert t2._row_of["d7"] == 30 and t2.avro_chunk == t.avro_chunk
+    q = vecs[7:8]
+    a, b = vector_search_agg(t, "embedding", q, 5)[0], vector_search_agg(t2, "embedding", q, 5)[0]
+    assert [(h.row, h.score) for h in a] == [(h.row, h.score) for h in b] and all(h.row != 7 for h in b)
+    t2.upsert_many(["d3"], ["c3 newer"], g.standard_normal((1, 64)).astype(np.float32))    # upserts keep working after resume
+    assert t2._row_of["d3"] == 31 and (t2.index.bits[3] == 0).all()
+    raw = vector_search_agg(t, "embedding", q, 3)[0]
+    atl = vector_search_agg(t, "embedding", q, 3, score_mode="atlas")[0]
+    assert [h.row for h in raw] == [h.row for h in atl]
+    assert all(abs(x.score - atlas_score(y.score)) < 1e-12 and 0 <= x.score <= 1 for x, y in zip(atl, raw))
+    with pytest.raises(ValueError):
+        vector_search_agg(t, "embedding", q, 3, score_mode="dot")

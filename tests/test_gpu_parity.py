@@ -428,3 +428,24 @@ def test_host_slots_submit_wait(bf):
     with pytest.raises(capi.SaError):
         capi.check(ix.lib.sa_search_host_submit(ix._h, 2, f32[1].ctypes.data, 17, k), "submit")
     ix.close()
+
+
+def test_index_snapshot_restore(bf, tmp_path):
+    """Checkpoint / resume of the HBM half: a restored index answers exactly like the original, and keeps growing."""
+    from qsa_b200.engine import VectorIndex
+    dim, n = 192, 7000
+    c = bf.synth_rows(95, 0, n, dim)
+    q = bf.synth_queries(96, 50, dim, c)
+    ix = VectorIndex(dim=dim, capacity=8000, max_batch=64, max_k=10)
+    ix.append_bf16_bits(c[:6000])
+    ix.delete_rows([5, 17])
+    assert ix.snapshot(str(tmp_path / "index.npz")) == 6000
+    ix2 = VectorIndex(dim=dim, capacity=8000, max_batch=64, max_k=10)
+    assert ix2.restore(str(tmp_path / "index.npz")) == 6000 and len(ix2) == 6000
+    ref = c[:6000].copy(); ref[[5, 17]] = 0
+    check(ix2, q, ref, 10)
+    ix2.append_bf16_bits(c[6000:])
+    check(ix2, q, np.concatenate([ref, c[6000:]]), 10)
+    with pytest.raises(ValueError):
+        VectorIndex(dim=128, capacity=8000, max_batch=64, max_k=10).restore(str(tmp_path / "index.npz"))
+    ix.close(); ix2.close()
