@@ -205,6 +205,33 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------
+def collective_preheat(step, seconds, world, sync, all_reduce_max=None, chunk=4):
+    """Run `step` back to back for about `seconds`, untimed.  With several ranks every step contains collectives, so
+    all ranks MUST run the same number of steps: the loop proceeds in chunks of `chunk` steps and the decision to stop
+    is itself a collective (max over ranks of "my time is up"), never a per-rank clock.  Returns the steps run."""
+    n = 0
+    if seconds <= 0:
+        return n
+    t0 = time.perf_counter()
+    while True:
+        for _ in range(chunk):
+            step()
+        n += chunk
+        sync()
+        up = 1 if time.perf_counter() - t0 >= seconds else 0
+        if world > 1:
+            up = all_reduce_max(up)
+        if up:
+            return n
+
+
+def _all_reduce_max_flag(flag, dist, torch):
+    t = torch.tensor([flag], device="cuda", dtype=torch.int32)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return int(t.item())
+
+
+
 def fill_corpus(ix, n_local, dim, seed):
     """Synthetic corpus generated on the device (Philox) straight into the bf16 rows, then committed."""
     import torch
@@ -274,13 +301,8 @@ def run_b200(a):
 
     # ---- preheat (untimed): a 1 kW part boosts for the first second of load and then settles at its power cap; the
     # roofline denominator (cuBLAS, 4 s back to back) is a settled number, so settle before timing anything
-    t_pre = time.perf_counter()
-    n_pre = 0
-    while time.perf_counter() - t_pre < a.preheat:
-        out = step_device()
-        n_pre += 1
-        if n_pre % 4 == 0:
-            torch.cuda.synchronize()
+    collective_preheat(step_device, a.preheat, world, torch.cuda.synchronize,
+                       (lambda flag: _all_reduce_max_flag(flag, dist, torch)) if world > 1 else None)
     # ---- warm-up
     for _ in range(a.warmup):
         out = step_device()
