@@ -129,6 +129,16 @@ int sa_debug_tile_dots(sa_engine* e, const void* q_bf16_dev, int nq, int tile, i
 int sa_debug_plan(int num_sms, int nq, int cta_group, int num_tiles, int max_launch_qblocks, int allow_qpu2, int* out,
                   int max_out, int* n_launches);
 
+/* Test hooks over the kernels' pure helper functions, compiled for the host (no GPU needed): the order-preserving
+ * score keys of the shared thresholds, the fp32 -> bf16 rounding of the ingest path, the (score, row) merge keys, and
+ * the sorted-list insertion rule of the epilogue fed value by value (floor_after[i], if given and > -inf, is a shared
+ * bound that becomes visible just before value i). */
+int sa_debug_float_keys(const float* x, int n, uint32_t* key, float* back, float* below);
+int sa_debug_bf16_round(const float* x, int n, uint16_t* bits, float* back);
+int sa_debug_merge_keys(const float* score, const int32_t* row, int n, uint64_t* key, int32_t* row_back);
+int sa_debug_list_insert(const float* score, const int32_t* row, int n, int list_len, const float* floor_after,
+                         float* out_score, int32_t* out_row);
+
 /* Pinned host memory for callers that want truly asynchronous staging. */
 int sa_host_alloc(void** out, uint64_t bytes);
 int sa_host_free(void* p);

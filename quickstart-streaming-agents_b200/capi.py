@@ -25,7 +25,8 @@ EXPORTS = (
     "sa_version", "sa_strerror", "sa_last_error", "sa_engine_create", "sa_engine_destroy", "sa_corpus_bind",
     "sa_corpus_commit", "sa_corpus_append_f32", "sa_corpus_append_host_f32", "sa_corpus_reset", "sa_corpus_rows",
     "sa_search", "sa_search_f32", "sa_search_host", "sa_search_host_submit", "sa_search_host_wait", "sa_merge_shards", "sa_last_timing", "sa_timing_mean", "sa_set_option",
-    "sa_get_info", "sa_debug_tile_dots", "sa_debug_plan", "sa_host_alloc", "sa_host_free",
+    "sa_get_info", "sa_debug_tile_dots", "sa_debug_plan", "sa_debug_float_keys", "sa_debug_bf16_round",
+    "sa_debug_merge_keys", "sa_debug_list_insert", "sa_host_alloc", "sa_host_free",
 )
 
 
@@ -78,6 +79,10 @@ def load() -> C.CDLL:
         "sa_get_info": (i32, [vp, C.c_char_p, C.POINTER(i64)]),
         "sa_debug_tile_dots": (i32, [vp, vp, i32, i32, i32, vp, vp]),
         "sa_debug_plan": (i32, [i32, i32, i32, i32, i32, i32, C.POINTER(i32), i32, C.POINTER(i32)]),
+        "sa_debug_float_keys": (i32, [vp, i32, vp, vp, vp]),
+        "sa_debug_bf16_round": (i32, [vp, i32, vp, vp]),
+        "sa_debug_merge_keys": (i32, [vp, vp, i32, vp, vp]),
+        "sa_debug_list_insert": (i32, [vp, vp, i32, i32, vp, vp, vp]),
         "sa_host_alloc": (i32, [C.POINTER(vp), u64]),
         "sa_host_free": (i32, [vp]),
     }

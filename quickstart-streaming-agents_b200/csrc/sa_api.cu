@@ -381,6 +381,34 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
 
 }  // namespace
 
+namespace {
+template <int kKL>
+void run_list(const float* score, const int32_t* row, int n, const float* floor_after, float* out_sc, int32_t* out_id) {
+  // The epilogue's per-value rule, value by value: insert when s > max(own kKL-th best, shared floor).
+  float sc[kKL];
+  int id[kKL];
+  for (int i = 0; i < kKL; ++i) {
+    sc[i] = -INFINITY;
+    id[i] = -1;
+  }
+  float thr_floor = -INFINITY, thr = -INFINITY;
+  for (int i = 0; i < n; ++i) {
+    if (floor_after && floor_after[i] > -INFINITY) {  // a bound published by another tile lane becomes visible
+      thr_floor = sa::float_below(floor_after[i]);
+      thr = fmaxf(thr, thr_floor);
+    }
+    if (score[i] > thr) {
+      sa::list_insert<kKL>(sc, id, score[i], row[i]);
+      thr = fmaxf(sc[kKL - 1], thr_floor);
+    }
+  }
+  for (int i = 0; i < kKL; ++i) {
+    out_sc[i] = sc[i];
+    out_id[i] = id[i];
+  }
+}
+}  // namespace
+
 extern "C" {
 
 int sa_version(void) { return 100; }
@@ -872,6 +900,44 @@ int sa_debug_plan(int num_sms, int nq, int cta_group, int num_tiles, int max_lau
     out[5 * i + 4] = plan[i].qpu;
   }
   *n_launches = static_cast<int>(plan.size());
+  return SA_OK;
+}
+
+// ---- host-side test hooks over the pure device helpers (compiled __host__ __device__; no GPU involved) ----------
+int sa_debug_float_keys(const float* x, int n, uint32_t* key, float* back, float* below) {
+  if (!x || !key || !back || !below || n < 0) return fail(SA_ERR_ARG, "bad argument");
+  for (int i = 0; i < n; ++i) {
+    key[i] = sa::float_to_key(x[i]);
+    back[i] = sa::key_to_float(key[i]);
+    below[i] = sa::float_below(x[i]);
+  }
+  return SA_OK;
+}
+
+int sa_debug_bf16_round(const float* x, int n, uint16_t* bits, float* back) {
+  if (!x || !bits || !back || n < 0) return fail(SA_ERR_ARG, "bad argument");
+  for (int i = 0; i < n; ++i) {
+    bits[i] = static_cast<uint16_t>(sa::f32_to_bf16_bits(x[i]));
+    back[i] = sa::bf16_bits_to_f32(bits[i]);
+  }
+  return SA_OK;
+}
+
+int sa_debug_merge_keys(const float* score, const int32_t* row, int n, uint64_t* key, int32_t* row_back) {
+  if (!score || !row || !key || !row_back || n < 0) return fail(SA_ERR_ARG, "bad argument");
+  for (int i = 0; i < n; ++i) {
+    key[i] = sa::make_key(score[i], row[i]);
+    row_back[i] = sa::key_row(key[i]);
+  }
+  return SA_OK;
+}
+
+int sa_debug_list_insert(const float* score, const int32_t* row, int n, int list_len, const float* floor_after,
+                         float* out_score, int32_t* out_row) {
+  if (!score || !row || !out_score || !out_row || n < 0) return fail(SA_ERR_ARG, "bad argument");
+  if (list_len == 16) run_list<16>(score, row, n, floor_after, out_score, out_row);
+  else if (list_len == 32) run_list<32>(score, row, n, floor_after, out_score, out_row);
+  else return fail(SA_ERR_ARG, "list_len must be 16 or 32");
   return SA_OK;
 }
 

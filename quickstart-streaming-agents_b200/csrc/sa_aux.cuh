@@ -4,13 +4,32 @@
 #pragma once
 #include <cstdint>
 #include <cmath>
+#include <cstring>
 
 namespace sa {
 
-__device__ __forceinline__ float bf16_bits_to_f32(uint32_t b) { return __uint_as_float(b << 16); }
+__host__ __device__ __forceinline__ uint32_t aux_f32_bits(float f) {
+#ifdef __CUDA_ARCH__
+  return __float_as_uint(f);
+#else
+  uint32_t u;
+  memcpy(&u, &f, sizeof u);
+  return u;
+#endif
+}
+__host__ __device__ __forceinline__ float aux_bits_f32(uint32_t u) {
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  float f;
+  memcpy(&f, &u, sizeof f);
+  return f;
+#endif
+}
+__host__ __device__ __forceinline__ float bf16_bits_to_f32(uint32_t b) { return aux_bits_f32(b << 16); }
 // Round-to-nearest-even fp32 -> bf16 bit pattern (NaN kept quiet); same rule as the oracle's numpy code.
-__device__ __forceinline__ uint32_t f32_to_bf16_bits(float f) {
-  uint32_t u = __float_as_uint(f);
+__host__ __device__ __forceinline__ uint32_t f32_to_bf16_bits(float f) {
+  uint32_t u = aux_f32_bits(f);
   if ((u & 0x7fffffffu) > 0x7f800000u) return (u >> 16) | 0x40u;
   return (u + 0x7fffu + ((u >> 16) & 1u)) >> 16;
 }
@@ -76,12 +95,12 @@ __global__ void sa_convert_rows_kernel(const float* __restrict__ src, uint16_t* 
 }
 
 // Order-preserving map: (score desc, row asc)  <=>  key desc.
-__device__ __forceinline__ unsigned long long make_key(float s, int row) {
-  uint32_t u = __float_as_uint(s);
+__host__ __device__ __forceinline__ unsigned long long make_key(float s, int row) {
+  uint32_t u = aux_f32_bits(s);
   u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
   return (static_cast<unsigned long long>(u) << 32) | static_cast<uint32_t>(~static_cast<uint32_t>(row));
 }
-__device__ __forceinline__ int key_row(unsigned long long k) { return static_cast<int>(~static_cast<uint32_t>(k)); }
+__host__ __device__ __forceinline__ int key_row(unsigned long long k) { return static_cast<int>(~static_cast<uint32_t>(k)); }
 
 struct MergeParams {
   const float* part_score;  // [grid CTAs][128][qpu][kKL] from the scan

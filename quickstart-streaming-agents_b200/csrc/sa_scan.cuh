@@ -16,6 +16,7 @@
 #pragma once
 #include "sm100_ptx.cuh"
 #include <cmath>
+#include <cstring>
 
 namespace sa {
 
@@ -62,28 +63,51 @@ struct ScanParams {
   int dbg_tile;
 };
 
+// Bit casts usable on both sides of the compiler: the device path is the intrinsic, the host path (used only by the
+// CPU unit tests through sa_debug_*) is a memcpy.
+__host__ __device__ __forceinline__ unsigned f32_bits(float f) {
+#ifdef __CUDA_ARCH__
+  return __float_as_uint(f);
+#else
+  unsigned u;
+  memcpy(&u, &f, sizeof u);
+  return u;
+#endif
+}
+__host__ __device__ __forceinline__ float bits_f32(unsigned u) {
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  float f;
+  memcpy(&f, &u, sizeof f);
+  return f;
+#endif
+}
+
 // Order-preserving float <-> unsigned key (larger float <=> larger key; key 0 is below every float).
-__device__ __forceinline__ unsigned float_to_key(float f) {
-  const unsigned u = __float_as_uint(f);
+__host__ __device__ __forceinline__ unsigned float_to_key(float f) {
+  const unsigned u = f32_bits(f);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
-__device__ __forceinline__ float key_to_float(unsigned k) {
-  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+__host__ __device__ __forceinline__ float key_to_float(unsigned k) {
+  return bits_f32((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 // The largest float strictly less than x (x finite): `s > float_below(x)` <=> `s >= x`.
-__device__ __forceinline__ float float_below(float x) {
-  const int b = __float_as_int(x);
-  if (x > 0.f) return __int_as_float(b - 1);
-  if (x < 0.f) return __int_as_float(b + 1);
-  return __int_as_float(static_cast<int>(0x80000001u));  // below +-0: the smallest negative denormal
+__host__ __device__ __forceinline__ float float_below(float x) {
+  const int b = static_cast<int>(f32_bits(x));
+  if (x > 0.f) return bits_f32(static_cast<unsigned>(b - 1));
+  if (x < 0.f) return bits_f32(static_cast<unsigned>(b + 1));
+  return bits_f32(0x80000001u);  // below +-0: the smallest negative denormal
 }
 
 // Sorted (descending score, ascending row on ties) insertion into a register-resident list.
 // Precondition: s > sc[kKL-1].  Rows reach a thread in ascending order, so a strict compare keeps the
 // lower row index ahead of an equal score.
 template <int kKL>
-__device__ __forceinline__ void list_insert(float (&sc)[kKL], int (&id)[kKL], float s, int row) {
+__host__ __device__ __forceinline__ void list_insert(float (&sc)[kKL], int (&id)[kKL], float s, int row) {
+#ifdef __CUDA_ARCH__
 #pragma unroll
+#endif
   for (int i = kKL - 1; i > 0; --i) {
     const bool shift = s > sc[i - 1];
     const bool here = s > sc[i];

@@ -1,0 +1,98 @@
+"""The kernels' pure helper functions, compiled for the host and called through the C ABI (no GPU): the same source
+lines the device executes.  Covers the numeric rules parity rests on: fp32 -> bf16 rounding equals the oracle's, the
+order-preserving keys are monotone, and the epilogue's list rule returns exactly the top-KL by (score desc, row asc)."""
+import ctypes as C
+
+import numpy as np
+from hypothesis import given, settings, strategies as st
+
+from oracle import bruteforce as bf
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def test_bf16_rounding_equals_the_oracle(lib):
+    g = np.random.default_rng(0)
+    x = np.concatenate([g.standard_normal(200_000).astype(np.float32) * np.float32(10.0) ** g.integers(-30, 30, 200_000).astype(np.float32),
+                        np.array([0.0, -0.0, 1.0, 1.00390625, 1.005859375, 1.0078125, np.inf, -np.inf, 3.3895314e38, 1e-45, -1e-45],
+                                 dtype=np.float32)]).astype(np.float32)
+    bits = np.empty(len(x), np.uint16)
+    back = np.empty(len(x), np.float32)
+    assert lib.sa_debug_bf16_round(ptr(x), len(x), ptr(bits), ptr(back)) == 0
+    assert (bits == bf.f32_to_bf16_bits(x)).all()
+    assert (back.view(np.uint32) == bf.bf16_bits_to_f32(bits).view(np.uint32)).all()
+    nan = np.array([np.nan], np.float32)
+    assert lib.sa_debug_bf16_round(ptr(nan), 1, ptr(bits), ptr(back)) == 0 and np.isnan(back[0])
+
+
+def test_float_keys_are_order_preserving_and_invertible(lib):
+    g = np.random.default_rng(1)
+    x = np.concatenate([g.standard_normal(50_000).astype(np.float32) * np.float32(10.0) ** g.integers(-20, 20, 50_000).astype(np.float32),
+                        np.array([0.0, -0.0, np.inf, -np.inf, 1e-45, -1e-45, 3.4e38, -3.4e38], np.float32)]).astype(np.float32)
+    key = np.empty(len(x), np.uint32); back = np.empty(len(x), np.float32); below = np.empty(len(x), np.float32)
+    assert lib.sa_debug_float_keys(ptr(x), len(x), ptr(key), ptr(back), ptr(below)) == 0
+    assert (back.view(np.uint32) == x.view(np.uint32)).all() and (key > 0).all()
+    order = np.argsort(x, kind="stable")
+    xs, ks = x[order], key[order].astype(np.uint64)
+    assert ((np.diff(ks.astype(np.int64)) > 0) == (np.diff(xs) > 0))[np.diff(xs) != 0].all()     # x < y  <=>  key(x) < key(y)
+    fin = np.isfinite(x)
+    assert (below[fin] < x[fin]).all()
+    assert (np.nextafter(below[fin & (x != 0)], np.float32(np.inf)) == x[fin & (x != 0)]).all()   # nothing in between
+
+
+def test_merge_keys_order_by_score_then_lower_row(lib):
+    g = np.random.default_rng(2)
+    n = 20_000
+    s = (np.round(g.standard_normal(n), 2) + 0.0).astype(np.float32)   # many exact score ties (and no -0.0: keys order bits)
+    r = g.permutation(n).astype(np.int32)
+    key = np.empty(n, np.uint64); rb = np.empty(n, np.int32)
+    assert lib.sa_debug_merge_keys(ptr(s), ptr(r), n, ptr(key), ptr(rb)) == 0
+    assert (rb == r).all()
+    by_key = np.argsort(key)[::-1]
+    ref = np.lexsort((r, -s))
+    assert (by_key == ref).all()
+    empty = np.array([-np.inf], np.float32); er = np.array([-1], np.int32)
+    assert lib.sa_debug_merge_keys(ptr(empty), ptr(er), 1, ptr(key), ptr(rb)) == 0 and rb[0] == -1 and 0 < key[0] < key[1:].min()
+
+
+def run_list(lib, s, rows, kl, floor=None):
+    s = np.ascontiguousarray(s, np.float32); rows = np.ascontiguousarray(rows, np.int32)
+    out_s = np.empty(kl, np.float32); out_r = np.empty(kl, np.int32)
+    f = None if floor is None else ptr(np.ascontiguousarray(floor, np.float32))
+    assert lib.sa_debug_list_insert(ptr(s), ptr(rows), len(s), kl, f, ptr(out_s), ptr(out_r)) == 0
+    return out_s, out_r
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.lists(st.one_of(st.floats(width=32, allow_nan=False, allow_infinity=False, min_value=-4, max_value=4),
+                          st.sampled_from([0.5, 0.25, -1.0, float("nan")])), min_size=0, max_size=120),
+       st.sampled_from([16, 32]))
+def test_list_rule_keeps_the_top_kl_with_ties_to_the_lower_row(lib, scores, kl):
+    s = np.asarray(scores, np.float32)
+    rows = np.arange(100, 100 + len(s), dtype=np.int32)                # rows arrive in ascending order, as in the scan
+    got_s, got_r = run_list(lib, s, rows, kl)
+    ok = ~np.isnan(s)                                                  # NaN (masked rows) never enters
+    order = np.lexsort((rows[ok], -s[ok]))[:kl]
+    exp_s = np.full(kl, -np.inf, np.float32); exp_r = np.full(kl, -1, np.int32)
+    exp_s[:len(order)] = s[ok][order]; exp_r[:len(order)] = rows[ok][order]
+    assert (got_r == exp_r).all() and (got_s.view(np.uint32) == exp_s.view(np.uint32)).all()
+
+
+def test_shared_floor_drops_only_what_cannot_matter(lib):
+    """A bound x published by another lane (KL rows there score >= x) may drop rows scoring < x but must keep ties."""
+    g = np.random.default_rng(3)
+    s = np.round(g.standard_normal(400), 1).astype(np.float32)
+    rows = np.arange(400, dtype=np.int32)
+    x = np.float32(1.0)
+    floor = np.full(400, -np.inf, np.float32); floor[50] = x           # becomes visible before value 50
+    got_s, got_r = run_list(lib, s, rows, 16, floor)
+    full_s, full_r = run_list(lib, s, rows, 16)
+    keep = full_s >= x                                                 # everything at or above the bound is untouched
+    assert (got_r[keep] == full_r[keep]).all() and (got_s[keep] == full_s[keep]).all()
+    # exact semantics: rows seen after the bound became visible are admitted iff they score >= x (ties included)
+    admit = (rows < 50) | (s >= x)
+    exp_s, exp_r = run_list(lib, s[admit], rows[admit], 16)
+    assert (got_r == exp_r).all() and (got_s == exp_s).all()
+    assert ((s == x) & (rows >= 50)).sum() > 0                         # the data really contains ties with the bound
