@@ -106,6 +106,7 @@ struct sa_engine {
   float* h_stage = nullptr;     // pinned staging for host ingest
   int64_t stage_rows = 0;
   cudaStream_t own_stream = nullptr;
+  cudaEvent_t scratch_free = nullptr;  // recorded after every search: the scratch buffers are shared by all searches
 
   long long* dbg_times = nullptr;  // [num_sms][2] CTA start/end timestamps of the last scan launch (option "record_times")
   int opt_record_times = 0;
@@ -291,6 +292,9 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
   if (static_cast<int>(plan.size()) > kMaxLaunches)
     return fail(SA_ERR_CAPACITY, "batch needs %zu scan launches (max %d)", plan.size(), kMaxLaunches);
 
+  // The candidate lists, shared thresholds and drift counters are one set of scratch buffers: a search issued on
+  // another stream than the previous one must not start before that one has finished with them.
+  SA_CUDA(cudaStreamWaitEvent(st, e->scratch_free, 0));
   sa_engine::Timing& tm = e->ring[e->n_searches % kTimingRing];
   tm.launches = 0;
   tm.kernels = 0;
@@ -371,6 +375,7 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
     tm.kernels += 2;
   }
   SA_CUDA(cudaEventRecord(tm.ev_total[1], st));
+  SA_CUDA(cudaEventRecord(e->scratch_free, st));
   // Algorithmic work: corpus + inverse norms once per scan launch, queries, results.
   const double n = static_cast<double>(n_rows), d = e->dim, b = nq;
   tm.bytes = plan.size() * (n * d * 2.0 + n * 4.0) + b * d * 2.0 + b * k * 8.0;
@@ -482,6 +487,7 @@ int sa_engine_create(sa_engine** out, int device, int dim, int64_t capacity_rows
   SA_TRY(cudaHostAlloc(&e->h_stage, static_cast<size_t>(e->stage_rows) * dim * 4, cudaHostAllocDefault));
   // a blocking stream: ordered after work already queued on the legacy default stream (torch's default)
   SA_TRY(cudaStreamCreate(&e->own_stream));
+  SA_TRY(cudaEventCreateWithFlags(&e->scratch_free, cudaEventDisableTiming));
   SA_TRY(cudaMalloc(&e->lane_progress, sizeof(int) * e->num_sms));
   SA_TRY(cudaMalloc(&e->thr_shared, sizeof(unsigned) * e->num_sms * 128));
   SA_TRY(cudaMalloc(&e->dbg_times, sizeof(long long) * 2 * e->num_sms));
@@ -519,6 +525,7 @@ void sa_engine_destroy(sa_engine* e) {
   }
   cudaFreeHost(e->h_stage);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  if (e->scratch_free) cudaEventDestroy(e->scratch_free);
   cudaFree(e->lane_progress);
   cudaFree(e->thr_shared);
   cudaFree(e->dbg_times);
@@ -626,6 +633,7 @@ int sa_search_f32(sa_engine* e, const float* q_f32_dev, int nq, int k, float* ou
   if (nq <= 0 || nq > e->max_batch) return fail(SA_ERR_CAPACITY, "nq %d outside [1, max_batch %d]", nq, e->max_batch);
   SA_CUDA(cudaSetDevice(e->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  SA_CUDA(cudaStreamWaitEvent(st, e->scratch_free, 0));  // q_bf16 is scratch too: the previous search still reads it
   const long long threads = static_cast<long long>(nq) * 32;
   sa::sa_convert_rows_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(q_f32_dev, e->q_bf16,
                                                                                          nullptr, nq, e->dim);
