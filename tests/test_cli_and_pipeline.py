@@ -358,3 +358,45 @@ def test_table_checkpoint_resume_and_atlas_score(tmp_path):
     assert all(abs(x.score - atlas_score(y.score)) < 1e-12 and 0 <= x.score <= 1 for x, y in zip(atl, raw))
     with pytest.raises(ValueError):
         vector_search_agg(t, "embedding", q, 3, score_mode="dot")
+
+
+def test_sa_serve_cli_snapshot_resume_with_a_double(tmp_path, capsys, monkeypatch):
+    """`sa_serve --once --snapshot-dir`: the second run resumes from the checkpoint (no replay of `documents`, offsets
+    continue) and serves new queries.  The engine is replaced by an oracle-backed double so this runs without a GPU."""
+    import qsa_b200.engine as engine_mod
+    from scripts import sa_serve
+
+    class SnapIndex(OracleIndex):
+        def __init__(self, dim=1536, capacity=0, max_batch=0, max_k=0, device=None):
+            super().__init__(dim, capacity)
+
+        def snapshot(self, path):
+            np.savez(path, rows=self.bits)
+            return len(self.bits)
+
+        def restore(self, path):
+            self.bits = np.load(path)["rows"]
+            return len(self.bits)
+
+    monkeypatch.setattr(engine_mod, "VectorIndex", SnapIndex)
+    docs, logd, snap = tmp_path / "docs", str(tmp_path / "topics"), str(tmp_path / "ckpt")
+    write_docs(docs, 20)
+    assert publish_docs.main(["--docs-dir", str(docs), "--log-dir", logd]) == 0
+    assert lab2_publish_queries.main(["What about watermarks?", "--log-dir", logd]) == 0
+    capsys.readouterr()
+    assert sa_serve.main(["--log-dir", logd, "--once", "--snapshot-dir", snap]) == 0
+    first = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert first["documents"] == 21 and first["searches"] == 1
+    assert (tmp_path / "ckpt" / "columns.jsonl").exists() and (tmp_path / "ckpt" / "index.npz").exists()
+    # second process: nothing new on `documents`, one new query; the table comes from the checkpoint
+    assert lab2_publish_queries.main(["How do session windows work?", "--log-dir", logd]) == 0
+    capsys.readouterr()
+    assert sa_serve.main(["--log-dir", logd, "--once", "--snapshot-dir", snap]) == 0
+    cap = capsys.readouterr()
+    second = json.loads(cap.out.strip().splitlines()[-1])
+    assert "resumed 21 rows" in cap.err
+    assert second["documents"] == 0 and second["searches"] == 1 and second["responses"] == 1
+    c = Consumer({"log.dir": logd, "group.id": "t"}); c.subscribe(["search_results"])
+    rows = [Codec(logd).decode(m.value()) for m in c.consume(10, 0.0)]
+    assert [r["query"] for r in rows] == ["What about watermarks?", "How do session windows work?"]
+    assert all(r["document_id_1"] for r in rows)
