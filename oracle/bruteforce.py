@@ -1,7 +1,7 @@
 """CPU oracle for the hot path -- TEST INFRASTRUCTURE ONLY.
 
-Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may
-import this module; the product path (``quickstart-streaming-agents_b200``) never does and fails loudly when the
+Only ``tests/`` (incl. ``tests/harness/``), ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this module; the product path (``quickstart-streaming-agents_b200``) never does and fails loudly when the
 CUDA library is missing.
 
 PARITY UNPINNED.  The reference (confluentinc/quickstart-streaming-agents) contains no implementation of

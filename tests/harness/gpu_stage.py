@@ -1,11 +1,11 @@
 """Development harness: one staged hardware check per process (a device trap poisons the CUDA context, so each
-stage runs in its own interpreter under `timeout`).  Usage: python tools/gpu_stage.py <stage> [args]."""
+stage runs in its own interpreter under `timeout`).  Usage: python tests/harness/gpu_stage.py <stage> [args]."""
 import json
 import os
 import sys
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 

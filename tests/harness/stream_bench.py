@@ -6,7 +6,7 @@ the search stream keeps going; each search sees the prefix committed when it was
 steady-state QPS during ingest, ingest throughput, and the final-epoch parity check against the oracle on a sample.
 """
 import argparse, json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 from qsa_b200.engine import VectorIndex

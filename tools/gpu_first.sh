@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 L=gpurun_out/first.log
 : > $L
-run() { echo "=== $*" >> $L; timeout 300 python tools/gpu_stage.py "$@" >> $L 2>&1; echo "rc=$?" >> $L; }
+run() { echo "=== $*" >> $L; timeout 300 python tests/harness/gpu_stage.py "$@" >> $L 2>&1; echo "rc=$?" >> $L; }
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv >> $L 2>&1
 run dots 1 1024 1536 128
 run dots 1 700 768 100
