@@ -48,11 +48,11 @@ struct ScanParams {
   int num_tiles;          // ceil(n_rows / 256)
   int nqb;                // query blocks of 128*kCG rows
   int tl_count;           // tile lanes (TL)
-  float* part_score;      // [gridDim.x][128][kKL]
-  int* part_idx;          // [gridDim.x][128][kKL]
+  float* part_score;      // [gridDim.x][128][kQPU][kKL]
+  int* part_idx;          // [gridDim.x][128][kQPU][kKL]
   int corpus_evict_first; // 1: corpus tiles are read by a single query block -> stream them through L2
-  int* lane_progress;     // [tl_count][nqb] tiles whose loads each unit has issued (zeroed before launch), or nullptr
-  int unit_map;           // 0: unit = tl*nqb + qb (lane-mates adjacent), 1: unit = qb*TL + tl (lane-mates TL apart)
+  int* lane_progress;     // [tl_count][nslots] tiles whose loads each unit has issued (zeroed before launch), or nullptr
+  int unit_map;           // 0: unit = tl*nslots + slot (lane-mates adjacent), 1: unit = slot*TL + tl (lane-mates TL apart)
   int max_drift;          // lead (in tiles) over the slowest lane-mate that is not paced
   int pace_gain;          // SM cycles of delay per K-slice issue per tile of lead beyond max_drift (0 = free-running)
   int pace_max;           // cap of that delay
