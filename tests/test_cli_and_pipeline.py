@@ -400,3 +400,33 @@ def test_sa_serve_cli_snapshot_resume_with_a_double(tmp_path, capsys, monkeypatc
     rows = [Codec(logd).decode(m.value()) for m in c.consume(10, 0.0)]
     assert [r["query"] for r in rows] == ["What about watermarks?", "How do session windows work?"]
     assert all(r["document_id_1"] for r in rows)
+
+
+def test_config1_two_thousand_docs_plumbing_on_cpu(tmp_path):
+    """BASELINE.json configs[0]: ~2k Lab2-style chunks published with publish_docs, 32 questions with publish_queries,
+    numpy cosine top-10 on the CPU (the oracle, standing in for the GPU index in this no-GPU plumbing case), first three
+    results on `search_results` in the reference's column layout."""
+    from oracle import bruteforce as bf
+    docs, logd = tmp_path / "docs", str(tmp_path / "topics")
+    write_docs(docs, 2047)                                   # + plain.md = 2048 chunks
+    assert publish_docs.main(["--docs-dir", str(docs), "--workers", "8", "--log-dir", logd]) == 0
+    questions = [f"Question {i}: tell me about {TOPICS[i % len(TOPICS)]} number {i * 61 % 2047}" for i in range(32)]
+    for q in questions:
+        assert lab2_publish_queries.main([q, "--log-dir", logd]) == 0
+    idx = OracleIndex(1536)
+    table = VectorTable(idx)
+    emb = StubEmbedder(1536)
+    pipe = Lab2Pipeline(logd, table, embedder=emb, k=10, max_batch=256)
+    pipe.run_until_idle()
+    assert len(table) == 2048 and pipe.stats["searches"] == 32 and pipe.stats["responses"] == 32
+    c = Consumer({"log.dir": logd, "group.id": "t"}); c.subscribe(["search_results"])
+    rows = [Codec(logd).decode(m.value()) for m in c.consume(100, 0.0)]
+    assert [r["query"] for r in rows] == questions
+    # independent numpy check of the top-10 -> the topic carries its first three
+    qv = bf.f32_to_bf16_bits(np.stack([emb.embed(q) for q in questions]))
+    s, i = bf.cosine_topk_f64(qv, idx.bits, 10)
+    for r, row in enumerate(rows):
+        assert [row[f"document_id_{j}"] for j in (1, 2, 3)] == [table.document_id[x] for x in i[r, :3]]
+        assert abs(row["score_1"] - s[r, 0]) < 1e-6 and row["score_1"] >= row["score_2"] >= row["score_3"]
+    hits = vector_search_agg(table, "embedding", emb.embed(questions[0]), 10)[0]
+    assert [h.row for h in hits] == i[0].tolist()
