@@ -134,7 +134,8 @@ def run_reference(a):
             vals.append(cpu_sample_run(q, prepared, a.k, a.rows)[0])
         dt = time.perf_counter() - t0
     v = float(np.median(vals))
-    sample = f"{nq} queries x {rows} rows per step (of {a.batch} x {a.rows}); QPS scaled by rows"
+    sample = (f"{nq} queries x {rows} rows per step (of {a.batch} x {a.rows}); QPS scaled by rows; top-k selection: "
+              + ("oracle/topk.c on all cores" if bf._topk_lib() is not None else "numpy argpartition"))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "strong",
@@ -466,7 +467,8 @@ def run_b200(a):
                 v, dt = cpu_sample_run(qs, prepared, k, n_total)
             result["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                       "sample": f"{nsq} queries x {sum(len(c) for _, c, _ in prepared)} rows in {dt:.1f}s "
-                                                f"(numpy fp32 sgemm brute force over unit-norm fp32 rows in RAM, "
+                                                f"(numpy fp32 sgemm brute force over unit-norm fp32 rows in RAM, top-k selection "
+                                                f"{'oracle/topk.c on all cores' if bf._topk_lib() is not None else 'numpy argpartition'}, "
                                                 f"QPS scaled to {n_total} rows)"}
         except Exception as exc:   # the measured line must still be printed; say what could not be checked
             result.setdefault("recall", None)

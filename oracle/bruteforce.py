@@ -195,19 +195,45 @@ def prepare_chunks_f32(c_chunks):
     return out
 
 
-def cosine_topk_sgemm_prepared(q_bits: np.ndarray, prepared, k: int):
-    """The timed CPU baseline: numpy brute force over a corpus that already sits in RAM as unit-norm fp32 rows
-    (``prepare_chunks_f32``).  Per chunk: one sgemm (all BLAS threads) + argpartition top-k + running merge."""
+_TOPK_LIB = None
+
+
+def _topk_lib():
+    """oracle/_build/liboracle_topk.so (oracle/topk.c, built by __graft_entry__.build()), or None when absent."""
+    global _TOPK_LIB
+    if _TOPK_LIB is None:
+        import ctypes
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "liboracle_topk.so")
+        _TOPK_LIB = False
+        if os.path.exists(path):
+            lib = ctypes.CDLL(path)
+            lib.oracle_topk_merge_f32.restype = None
+            lib.oracle_topk_merge_f32.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
+                                                  ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+            _TOPK_LIB = lib
+    return _TOPK_LIB or None
+
+
+def cosine_topk_sgemm_prepared(q_bits: np.ndarray, prepared, k: int, use_c_topk: bool = True):
+    """The timed CPU baseline: brute force over a corpus that already sits in RAM as unit-norm fp32 rows
+    (``prepare_chunks_f32``).  Per chunk: one sgemm (all BLAS threads) + top-k selection + running merge; the selection
+    runs on all cores through oracle/topk.c when that is built, else numpy argpartition (one thread)."""
     q = bf16_bits_to_f32(q_bits)
     qn = np.sqrt((q.astype(np.float64) ** 2).sum(axis=1)).astype(np.float32)
     qh = q / np.where(qn > 0, qn, 1)[:, None]
     nq = q.shape[0]
     best_s = np.full((nq, k), -np.inf, dtype=np.float32)
     best_i = np.full((nq, k), -1, dtype=np.int64)
+    lib = _topk_lib() if use_c_topk else None
     for lo, c, zero in prepared:
         s = qh @ c.T
         if zero.any():
             s[:, zero] = -np.inf
+        if lib is not None:
+            s = np.ascontiguousarray(s, dtype=np.float32)
+            lib.oracle_topk_merge_f32(s.ctypes.data, nq, s.shape[1], k, lo, best_s.ctypes.data, best_i.ctypes.data)
+            continue
         m = s.shape[1]
         kk = min(k, m)
         part = np.argpartition(s, m - kk, axis=1)[:, m - kk :]

@@ -107,3 +107,27 @@ def test_oracle_agrees_with_independent_cosine_implementations():
         assert (order == i).all()
     ts, ti = torch.topk(torch.from_numpy(sim_scipy), k, dim=1)
     assert (ti.numpy() == i).all()
+
+
+def test_c_topk_helper_equals_numpy_selection():
+    """oracle/topk.c (the multi-core selection of the CPU baseline) against the numpy path: ties to the lower row,
+    -inf rows never returned, running merge across chunks, k larger than the rows available."""
+    import __graft_entry__ as ge
+    ge.build_oracle_helper()
+    bf._TOPK_LIB = None
+    assert bf._topk_lib() is not None
+    c = bf.synth_rows(7, 0, 30000, 128)
+    c[17] = 0
+    c[900] = c[5]; c[20001] = c[5]
+    q = bf.synth_queries(9, 40, 128, c)
+    q[0] = c[5]
+    for cuts in ([0, 30000], [0, 11000, 20500, 30000], [0, 7, 30000]):
+        prep = bf.prepare_chunks_f32([(a, c[a:b]) for a, b in zip(cuts[:-1], cuts[1:])])
+        for k in (1, 10, 28):
+            s1, i1 = bf.cosine_topk_sgemm_prepared(q, prep, k, use_c_topk=False)
+            s2, i2 = bf.cosine_topk_sgemm_prepared(q, prep, k, use_c_topk=True)
+            assert (i1 == i2).all() and (s1 == s2).all()
+    assert i2[0, :3].tolist() == [5, 900, 20001] and 17 not in i2
+    tiny = bf.prepare_chunks_f32([(0, c[:4])])
+    s3, i3 = bf.cosine_topk_sgemm_prepared(q[:3], tiny, 10, use_c_topk=True)
+    assert (i3[:, 4:] == -1).all() and np.isneginf(s3[:, 4:]).all() and (np.sort(i3[:, :4], axis=1) == np.arange(4)).all()
