@@ -31,12 +31,12 @@ typedef enum sa_status {
   SA_OK = 0,
   SA_ERR_CUDA = -1,     /* a CUDA runtime / driver call failed */
   SA_ERR_ARG = -2,      /* bad argument (null, range, alignment, dim % 64 != 0, k > max_k ...) */
-  SA_ERR_COMM = -3,     /* reserved for collective errors (the all-gather itself runs in torch.distributed) */
+  SA_ERR_COMM = -3,     /* NCCL could not be loaded / a collective call failed (sa_comm_*) */
   SA_ERR_CAPACITY = -4, /* append past capacity_rows, batch past max_batch */
   SA_ERR_DEVICE = -5    /* device is not compute capability 10.x */
 } sa_status;
 
-#define SA_MAX_K 28 /* candidate lists hold k + 4 entries, at most 32 */
+#define SA_MAX_K 28 /* candidate lists hold 16 (k <= 12) or 32 entries per tile lane */
 #define SA_HOST_SLOTS 2 /* host-buffer searches that may be in flight at once (sa_search_host_submit) */
 
 int sa_version(void);
@@ -93,10 +93,56 @@ int sa_search_host(sa_engine* e, const float* q_f32_host, int nq, int k, float* 
 int sa_search_host_submit(sa_engine* e, int slot, const float* q_f32_host, int nq, int k);
 int sa_search_host_wait(sa_engine* e, int slot, float* out_score_host, int32_t* out_idx_host);
 
-/* --- multi-GPU: after each rank searched its row shard and the per-rank (score64, global row) lists were
- *     all-gathered into [n_shards x nq x k] buffers, merge to the global top-k. --- */
+/* --- multi-GPU: the corpus is row-sharded, every GPU searches its shard with the same single-GPU
+ *     path, the per-shard results cross NVLink in ONE all-gather of packed (cosine f64, global row) lists -- nq*k*16 bytes
+ *     per rank -- and every rank merges them to the global top-k by (cosine desc, global row asc).  This is the whole of
+ *     what the sharded VECTOR_SEARCH_AGG (main.tf:292) needs; there is no all-reduce and no all-to-all. ------------------ */
+typedef struct sa_hit {
+  double score; /* cosine, float64 */
+  int64_t row;  /* global row = shard-local row + row_offset, -1 = no row */
+} sa_hit;
+
+/* This shard's results in exchange format (device buffer [nq x k]), e.g. for a caller-run collective. */
+int sa_search_hits(sa_engine* e, const void* q_bf16_dev, int nq, int k, int64_t row_offset, sa_hit* out_hits_dev,
+                   uintptr_t stream);
+/* Merge gathered hit lists [n_shards x nq x k] into the global top-k: out_score [nq x k] fp32, out_row [nq x k] int64. */
+int sa_merge_hits(sa_engine* e, const sa_hit* hits_dev, int n_shards, int nq, int k, float* out_score_dev,
+                  int64_t* out_row_dev, uintptr_t stream);
+/* Older split form of the same merge (separate score / row arrays). */
 int sa_merge_shards(sa_engine* e, const double* score64_dev, const int64_t* global_idx_dev, int n_shards, int nq,
                     int k, float* out_score_dev, int64_t* out_idx_dev, uintptr_t stream);
+
+/* Communicator.  NCCL is loaded at run time (dlopen): the copy already loaded in the process if any (e.g. torch's), else
+ * the path given to sa_comm_set_library / $SA_NCCL_LIB, else the system libnccl.so.2.  Failures return SA_ERR_COMM. */
+#define SA_COMM_ID_BYTES 128
+typedef struct sa_comm sa_comm;
+int sa_comm_set_library(const char* path);
+int sa_comm_nccl_version(int* version, char* path_out, int path_cap);
+/* single process driving n_gpus devices (ncclCommInitAll); devices == NULL means 0 .. n_gpus-1 */
+int sa_comm_create(sa_comm** out, int n_gpus, const int* devices);
+/* one process per GPU: rank 0 calls sa_comm_unique_id, ships the 128 bytes to the others out of band, all call create_rank */
+int sa_comm_unique_id(void* id_out_128);
+int sa_comm_create_rank(sa_comm** out, int n_ranks, int rank, const void* id_128, int device);
+void sa_comm_destroy(sa_comm* c);
+int sa_comm_ranks(const sa_comm* c);
+
+/* One process per GPU: this rank's part of a sharded search (collective: every rank must call it with the same nq, k).
+ * Device form, asynchronous on `stream`: out_score [nq x k] fp32, out_row [nq x k] int64 global rows, same on all ranks. */
+int sa_sharded_search(sa_comm* c, sa_engine* e, const void* q_bf16_dev, int nq, int k, int64_t row_offset,
+                      float* out_score_dev, int64_t* out_row_dev, uintptr_t stream);
+/* Host-buffer form, split like sa_search_host_submit/_wait (slots 0 .. SA_HOST_SLOTS-1, two batches in flight). */
+int sa_sharded_search_host_submit(sa_comm* c, sa_engine* e, int slot, const float* q_f32_host, int nq, int k,
+                                  int64_t row_offset);
+int sa_sharded_search_host_wait(sa_comm* c, sa_engine* e, int slot, float* out_score_host, int64_t* out_row_host);
+
+/* Single process, all GPUs of the communicator: host fp32 queries in, merged host results out.  engines[g] lives on the
+ * communicator's device g and holds the shard whose first global row is shard_offsets[g].  sa_gather_merge blocks;
+ * the _submit/_wait pair keeps two batches in flight. */
+int sa_gather_merge(sa_comm* c, sa_engine* const* engines, const float* q_f32_host, int nq, int k,
+                    const int64_t* shard_offsets, float* out_score_host, int64_t* out_row_host);
+int sa_gather_merge_submit(sa_comm* c, sa_engine* const* engines, int slot, const float* q_f32_host, int nq, int k,
+                           const int64_t* shard_offsets);
+int sa_gather_merge_wait(sa_comm* c, sa_engine* const* engines, int slot, float* out_score_host, int64_t* out_row_host);
 
 /* --- observability ------------------------------------------------------------------------------------
  * CUDA-event times of the most recent search on this engine (synchronises on its last event):
@@ -112,11 +158,19 @@ int sa_timing_mean(sa_engine* e, int n, float* scan_ms_mean, float* total_ms_mea
  * drift control between query blocks that share corpus tiles (keeps a shared tile L2-resident so it crosses HBM
  * once): "max_drift" = unpaced lead in tiles (-1 auto), "pace_gain" = delay cycles per K-slice per extra tile
  * of lead (-1 auto, 0 off), "pace_max" = cap of that delay (-1 auto);
- * "qpu2" = 0 (default) | 1 (when it fills more SMs) | 2 (always): let a unit carry two query blocks,
  * "share_thresholds" = 1 | 0 (tile lanes exchange per-query top-k thresholds; default 1), "list_len" = 0 (auto) | 16 | 32,
- * "unit_map" = 0 | 1 (CTA -> (query block, tile lane) mapping), "record_times" = 0 | 1 (per-CTA timestamps). */
+ * "unit_map" = 0 | 1 (CTA -> (query block, tile lane) mapping), "record_times" = 0 | 1 (per-CTA timestamps),
+ * "profile" = 0 | 1 (run the scan's profiling build: per-CTA role wait/busy cycle counters, see sa_scan_profile),
+ * "force_fix" = 0 | 1 (test hook: route every (query, tile lane) through the exact fallback scan),
+ * "count_fix" = 0 | 1 (record how many (query, lane) pairs the last search sent to the fallback; costs a host sync). */
 int sa_set_option(sa_engine* e, const char* name, int64_t value);
-int sa_get_info(const sa_engine* e, const char* name, int64_t* value); /* "num_sms", "dim", "capacity", "n_rows" */
+/* "num_sms", "dim", "capacity", "n_rows", "max_batch", "max_k", "last_grid", "last_fix_entries" (with "count_fix"),
+ * "eps_rel_e12" (the certificate's error bound per unit |q|, times 1e12). */
+int sa_get_info(const sa_engine* e, const char* name, int64_t* value);
+/* Per-CTA profile records of the last scan launch run with "profile" = 1 (synchronises the device): out_host receives
+ * n_ctas x 8 int64 {TMA producer wait for a free slot, MMA issuer wait for data, MMA issuer wait for the epilogue,
+ * epilogue wait for the MMA, epilogue busy, epilogue 32-column chunks on the insertion path, CTA lifetime, tiles}, SM cycles. */
+int sa_scan_profile(sa_engine* e, int64_t* out_host, int max_ctas, int* n_ctas);
 
 /* Test hook: raw fp32 Q.C^T accumulators of one 256-row corpus tile for the first nq queries,
  * out_dots_dev is [ceil(nq/(128*cg))*128*cg x 256].  Runs the scan kernel's debug instantiation. */
@@ -124,20 +178,20 @@ int sa_debug_tile_dots(sa_engine* e, const void* q_bf16_dev, int nq, int tile, i
                        uintptr_t stream);
 
 /* Test hook (pure host logic, no GPU needed): how a batch of nq queries is split into scan launches on a device
- * with num_sms SMs.  out receives up to max_out rows of {first query, queries, query blocks, tile lanes,
- * query blocks per unit}. */
-int sa_debug_plan(int num_sms, int nq, int cta_group, int num_tiles, int max_launch_qblocks, int allow_qpu2, int* out,
-                  int max_out, int* n_launches);
+ * with num_sms SMs.  out receives up to max_out rows of {first query, queries, query blocks, tile lanes}. */
+int sa_debug_plan(int num_sms, int nq, int cta_group, int num_tiles, int max_launch_qblocks, int* out, int max_out,
+                  int* n_launches);
 
 /* Test hooks over the kernels' pure helper functions, compiled for the host (no GPU needed): the order-preserving
  * score keys of the shared thresholds, the fp32 -> bf16 rounding of the ingest path, the (score, row) merge keys, and
- * the sorted-list insertion rule of the epilogue fed value by value (floor_after[i], if given and > -inf, is a shared
- * bound that becomes visible just before value i). */
+ * the epilogue's list rule fed exactly as the kernel feeds it, in chunks of 32 consecutive values (floor_after[i], if
+ * given and > -inf, is a shared bound that becomes visible at the start of the chunk holding value i); out_drop (optional)
+ * receives the "dropped" bound: the largest score the list saw and does not hold. */
 int sa_debug_float_keys(const float* x, int n, uint32_t* key, float* back, float* below);
 int sa_debug_bf16_round(const float* x, int n, uint16_t* bits, float* back);
 int sa_debug_merge_keys(const float* score, const int32_t* row, int n, uint64_t* key, int32_t* row_back);
 int sa_debug_list_insert(const float* score, const int32_t* row, int n, int list_len, const float* floor_after,
-                         float* out_score, int32_t* out_row);
+                         float* out_score, int32_t* out_row, float* out_drop);
 
 /* Pinned host memory for callers that want truly asynchronous staging. */
 int sa_host_alloc(void** out, uint64_t bytes);

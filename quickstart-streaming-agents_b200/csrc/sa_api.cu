@@ -7,6 +7,8 @@
 
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types and prototypes only: the library itself is dlopen'ed (sa_comm_*), never linked
 
 #include <algorithm>
 #include <cstdarg>
@@ -65,6 +67,24 @@ int encode_rows_map(CUtensorMap* m, const void* base, uint64_t rows, int dim, in
   return SA_OK;
 }
 
+// Entry points switch to the engine's device and switch back on return, so a caller driving several GPUs from one
+// thread keeps its own current device.
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t rc = cudaSuccess;
+  explicit DeviceGuard(int dev) {
+    rc = cudaGetDevice(&prev);
+    if (rc == cudaSuccess && prev != dev) rc = cudaSetDevice(dev);
+    else if (rc == cudaSuccess) prev = -1;  // nothing to restore
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+#define SA_ON_DEVICE(dev)                                                                             \
+  DeviceGuard _dg(dev);                                                                              \
+  if (_dg.rc != cudaSuccess) return fail(SA_ERR_CUDA, "cudaSetDevice(%d) failed: %s", (dev), cudaGetErrorString(_dg.rc))
+
 constexpr int kMaxLaunches = 16;
 constexpr int kTimingRing = 16;
 constexpr int kHostSlots = SA_HOST_SLOTS;
@@ -88,15 +108,25 @@ struct sa_engine {
   // scratch (library-owned)
   float* part_score = nullptr;  // [num_sms][128][32]
   int* part_idx = nullptr;
+  float* part_drop = nullptr;   // [num_sms][128]
+  double* res64 = nullptr;      // [max_batch][max_k] internal result of a search: cosine (float64) ...
+  int* residx = nullptr;        // ... and shard-local row
+  sa::FixEntry* fix_entries = nullptr;  // [kMaxLaunches * num_sms * 128] work queue of the exact fallback scan
+  sa::FixQuery* fix_query = nullptr;    // [max_batch]
+  int* fix_counters = nullptr;          // [0] queue length, [1] CTAs done (both zero between searches)
   uint16_t* q_bf16 = nullptr;   // [max_batch][dim]
   float* q_f32 = nullptr;       // [max_batch][dim]  (host-path staging on device)
   float* res_score = nullptr;   // [max_batch][max_k]
   int* res_idx = nullptr;
+  sa::PackedHit* hits = nullptr;  // [max_batch][max_k] this shard's (cosine f64, global row) lists for the exchange
+  long long* res_row64 = nullptr; // [max_batch][max_k] merged global rows (sharded host path)
   // host-buffer path: pinned staging per slot (0,1 = public asynchronous slots, 2 = the blocking sa_search_host)
   struct HostSlot {
     float* h_q = nullptr;      // pinned [max_batch][dim]
     float* h_score = nullptr;  // pinned [max_batch][max_k]
     int* h_idx = nullptr;      // pinned
+    long long* h_row64 = nullptr;  // pinned [max_batch][max_k] (sharded searches return global rows)
+    bool sharded = false;
     cudaEvent_t done = nullptr;
     int nq = 0, k = 0;
     bool busy = false;
@@ -110,22 +140,28 @@ struct sa_engine {
 
   long long* dbg_times = nullptr;  // [num_sms][2] CTA start/end timestamps of the last scan launch (option "record_times")
   int opt_record_times = 0;
+  sa::ScanProf* prof = nullptr;    // [num_sms] per-CTA role counters of the last scan launch (option "profile")
+  int opt_profile = 0;
   int last_grid = 0;
-  unsigned* thr_shared = nullptr;  // [num_sms * 128] shared per-query thresholds of one scan launch (zeroed per launch)
+  // Shared per-query thresholds [thr_n] and drift counters [kMaxLaunches * num_sms] of the scan.  Both must be zero when
+  // a scan starts; every scan launch of a search uses its own slice and the search's last kernel re-zeroes what was used.
+  unsigned* thr_shared = nullptr;
+  int thr_n = 0;
+  int* lane_progress = nullptr;
+  bool scratch_dirty = false;  // a search failed between its first launch and its last: re-zero before the next one
   int opt_share_thresholds = 1;
-  int* lane_progress = nullptr;  // [num_sms] lockstep counters of the scan (zeroed per launch)
 
   // options
   int opt_cta_group = 0;
   int opt_max_launch_qblocks = 0;
-  int opt_max_drift = -1;  // -1 = auto (1 tile; 0 with two passes per tile)
+  int opt_max_drift = -1;  // -1 = auto (1 tile)
   int opt_pace_gain = -1;  // -1 = auto (16 cycles/tile for CTA pairs, 32 for single CTAs), 0 = off
   int opt_pace_max = -1;   // -1 = auto (8 x gain)
   int opt_unit_map = 0;
-  int opt_qpu2 = 0;       // 0 never (default), 1 when it shortens the tile walk, 2 always: two query blocks per unit.
-                          // Off by default: measured neutral under the power cap, and with two passes per tile a
-                          // lane-mate arrives later, so the shared tile is less reliably still in L2 (DRAM 1.07-1.4x)
-  int opt_list_len = 0;   // 0 = auto (16 when k <= 12, else 32)
+  int opt_list_len = 0;    // 0 = auto (16 when k <= 12, else 32)
+  int opt_force_fix = 0;   // test hook: every (query, lane) goes through the exact fallback scan
+  int64_t last_fix_entries = -1;  // option "count_fix": work-queue length of the last search (costs a host sync)
+  int opt_count_fix = 0;
 
   // timing: CUDA events of the most recent kTimingRing searches
   struct Timing {
@@ -147,33 +183,19 @@ struct LaunchPlan {
   int nq;   // queries in this launch
   int nqb;  // query blocks (of 128*cg)
   int tl;   // tile lanes
-  int qpu;  // query blocks per unit (1, or 2: two passes per tile, two candidate lists per thread)
 };
 
 // Tile lanes and walk length of one launch holding `per` query blocks.
-void lanes_for(int units, int per, int num_tiles, int qpu2_mode, int* tl, int* qpu, long* cost) {
-  const int tl1 = std::max(1, std::min(units / per, num_tiles));
-  const long cost1 = (num_tiles + tl1 - 1) / tl1;
+void lanes_for(int units, int per, int num_tiles, int* tl, long* cost) {
+  const int tl1 = std::max(1, std::min(std::min(units / per, num_tiles), sa::kMaxLanes));
   *tl = tl1;
-  *qpu = 1;
-  *cost = cost1;
-  if (qpu2_mode != 0 && per >= 2) {  // 0 never, 1 when it pays, 2 always (tests)
-    const int nslots = (per + 1) / 2;
-    const int tl2 = std::max(1, std::min(units / nslots, num_tiles));
-    const long cost2 = 2L * ((num_tiles + tl2 - 1) / tl2);
-    if (qpu2_mode == 2 || cost2 * 100 < cost1 * 99) {  // two passes per tile must buy more than 1 %
-      *tl = tl2;
-      *qpu = 2;
-      *cost = cost2;
-    }
-  }
+  *cost = (num_tiles + tl1 - 1) / tl1;
 }
 
 // Split the batch into scan launches.  A launch with nqb query blocks runs TL = floor(units / nqb) tile
 // lanes, each walking ceil(num_tiles / TL) tiles; pick the split that minimises the summed tile walks
 // (fewer launches win ties: every launch re-streams the corpus through HBM once).
-std::vector<LaunchPlan> plan_search(int num_sms, int max_launch_qblocks, int nq, int cg, int num_tiles,
-                                    int allow_qpu2) {
+std::vector<LaunchPlan> plan_search(int num_sms, int max_launch_qblocks, int nq, int cg, int num_tiles) {
   const int rows_per_qb = 128 * cg;
   const int units = num_sms / cg;
   const int nqb_total = (nq + rows_per_qb - 1) / rows_per_qb;
@@ -187,9 +209,9 @@ std::vector<LaunchPlan> plan_search(int num_sms, int max_launch_qblocks, int nq,
     int left = nqb_total;
     for (int i = 0; i < l; ++i) {
       const int per = (left + (l - i) - 1) / (l - i);
-      int tl, qpu;
+      int tl;
       long c;
-      lanes_for(units, per, num_tiles, allow_qpu2, &tl, &qpu, &c);
+      lanes_for(units, per, num_tiles, &tl, &c);
       cost += c;
       left -= per;
     }
@@ -208,7 +230,7 @@ std::vector<LaunchPlan> plan_search(int num_sms, int max_launch_qblocks, int nq,
     lp.q0 = qb0 * rows_per_qb;
     lp.nq = std::min(nq - lp.q0, per * rows_per_qb);
     lp.nqb = per;
-    lanes_for(units, per, num_tiles, allow_qpu2, &lp.tl, &lp.qpu, &c);
+    lanes_for(units, per, num_tiles, &lp.tl, &c);
     out.push_back(lp);
     qb0 += per;
     left -= per;
@@ -216,9 +238,9 @@ std::vector<LaunchPlan> plan_search(int num_sms, int max_launch_qblocks, int nq,
   return out;
 }
 
-template <int kCG, int kKL, int kQPU, bool kDebug>
+template <int kCG, int kKL, int kMode>
 int launch_scan(const CUtensorMap& tq, const CUtensorMap& tc, const sa::ScanParams& p, int grid, cudaStream_t st) {
-  auto kern = sa::sa_scan_kernel<kCG, kKL, kQPU, kDebug>;
+  auto kern = sa::sa_scan_kernel<kCG, kKL, kMode>;
   // per-device attribute; a few microseconds, so set it on every launch rather than caching per device
   SA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, sa::ScanCfg<kCG>::kSmemBytes));
   cudaLaunchConfig_t cfg = {};
@@ -237,19 +259,22 @@ int launch_scan(const CUtensorMap& tq, const CUtensorMap& tc, const sa::ScanPara
   return SA_OK;
 }
 
-int launch_scan_dispatch(int cg, int kl, int qpu, bool debug, const CUtensorMap& tq, const CUtensorMap& tc,
-                         const sa::ScanParams& p, int grid, cudaStream_t st) {
-  if (debug) {
-    if (cg == 1) return launch_scan<1, 16, 1, true>(tq, tc, p, grid, st);
-    return launch_scan<2, 16, 1, true>(tq, tc, p, grid, st);
+int launch_scan_dispatch(int cg, int kl, int mode, const CUtensorMap& tq, const CUtensorMap& tc, const sa::ScanParams& p,
+                         int grid, cudaStream_t st) {
+  if (mode == sa::kModeDots) {
+    if (cg == 1) return launch_scan<1, 16, sa::kModeDots>(tq, tc, p, grid, st);
+    return launch_scan<2, 16, sa::kModeDots>(tq, tc, p, grid, st);
   }
-  if (cg == 1 && kl == 16 && qpu == 1) return launch_scan<1, 16, 1, false>(tq, tc, p, grid, st);
-  if (cg == 1 && kl == 16 && qpu == 2) return launch_scan<1, 16, 2, false>(tq, tc, p, grid, st);
-  if (cg == 1 && kl == 32 && qpu == 1) return launch_scan<1, 32, 1, false>(tq, tc, p, grid, st);
-  if (cg == 2 && kl == 16 && qpu == 1) return launch_scan<2, 16, 1, false>(tq, tc, p, grid, st);
-  if (cg == 2 && kl == 16 && qpu == 2) return launch_scan<2, 16, 2, false>(tq, tc, p, grid, st);
-  if (cg == 2 && kl == 32 && qpu == 1) return launch_scan<2, 32, 1, false>(tq, tc, p, grid, st);
-  return fail(SA_ERR_ARG, "no scan instantiation for cta_group %d list %d qpu %d", cg, kl, qpu);
+  if (mode == sa::kModeProf) {
+    if (cg == 1 && kl == 16) return launch_scan<1, 16, sa::kModeProf>(tq, tc, p, grid, st);
+    if (cg == 2 && kl == 16) return launch_scan<2, 16, sa::kModeProf>(tq, tc, p, grid, st);
+    return fail(SA_ERR_ARG, "the profiling build of the scan exists for 16-entry lists only");
+  }
+  if (cg == 1 && kl == 16) return launch_scan<1, 16, sa::kModeProd>(tq, tc, p, grid, st);
+  if (cg == 1 && kl == 32) return launch_scan<1, 32, sa::kModeProd>(tq, tc, p, grid, st);
+  if (cg == 2 && kl == 16) return launch_scan<2, 16, sa::kModeProd>(tq, tc, p, grid, st);
+  if (cg == 2 && kl == 32) return launch_scan<2, 32, sa::kModeProd>(tq, tc, p, grid, st);
+  return fail(SA_ERR_ARG, "no scan instantiation for cta_group %d list %d", cg, kl);
 }
 
 int choose_cg(const sa_engine* e, int nq) {
@@ -274,31 +299,55 @@ int check_engine(const sa_engine* e) {
   return SA_OK;
 }
 
+// The scan's approximate score a = fp32_accumulate(q . c) * fl(1/|c|) against the exact e = <q, c>/|c|, both divided by
+// |q|:  fp32 accumulation of dim exact products, each addition off by at most one ulp of the running magnitude
+// (<= |q||c| by Cauchy-Schwarz): dim * 2^-23;  the inverse norm (fp32 sum of squares over dim/32 terms per lane + a
+// 5-level butterfly, one square root, one division) and the final multiply: (dim/64 + 6) * 2^-23, rounded up generously.
+// Measured worst case on adversarial inputs is ~100x smaller (tests/test_gpu_parity.py::test_scan_error_is_inside_eps).
+float scan_eps_rel(int dim) { return (1.0625f * dim + 16.0f) * 1.1920929e-07f; }
+
+int zero_scan_scratch(sa_engine* e, cudaStream_t st) {
+  SA_CUDA(cudaMemsetAsync(e->thr_shared, 0, sizeof(unsigned) * e->thr_n, st));
+  SA_CUDA(cudaMemsetAsync(e->lane_progress, 0, sizeof(int) * kMaxLaunches * e->num_sms, st));
+  SA_CUDA(cudaMemsetAsync(e->fix_counters, 0, sizeof(int) * 2, st));
+  return SA_OK;
+}
+
+// One search = per scan launch {scan kernel, merge/certify kernel}, then one fixup kernel (exact fallback scan of the
+// ambiguous (query, lane) pairs -- normally none -- and conversion of the internal result to the caller's arrays).
 int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_score, int32_t* out_idx,
-              double* out_score64, cudaStream_t st) {
+              double* out_score64, sa::PackedHit* out_packed, int64_t row_offset, cudaStream_t st) {
   if (nq <= 0 || nq > e->max_batch) return fail(SA_ERR_CAPACITY, "nq %d outside [1, max_batch %d]", nq, e->max_batch);
   if (k <= 0 || k > e->max_k) return fail(SA_ERR_ARG, "k %d outside [1, max_k %d]", k, e->max_k);
   if (!q_bf16 || !out_score || !out_idx) return fail(SA_ERR_ARG, "null buffer");
   if (reinterpret_cast<uintptr_t>(q_bf16) % 16) return fail(SA_ERR_ARG, "query buffer must be 16-byte aligned");
-  SA_CUDA(cudaSetDevice(e->device));
+  SA_ON_DEVICE(e->device);
 
   const int kl = e->opt_list_len ? e->opt_list_len : ((k + 4 <= 16) ? 16 : 32);
-  if (k + 4 > kl) return fail(SA_ERR_ARG, "k %d needs candidate lists longer than list_len %d", k, kl);
+  if (k > kl) return fail(SA_ERR_ARG, "k %d needs candidate lists longer than list_len %d", k, kl);
   const int64_t n_rows = e->n_rows;
   const int num_tiles = static_cast<int>((n_rows + sa::kBlockN - 1) / sa::kBlockN);
   const int cg = choose_cg(e, nq);
-  std::vector<LaunchPlan> plan = plan_search(e->num_sms, e->opt_max_launch_qblocks, nq, cg, std::max(num_tiles, 1),
-                                             kl == 16 ? e->opt_qpu2 : 0);
+  std::vector<LaunchPlan> plan = plan_search(e->num_sms, e->opt_max_launch_qblocks, nq, cg, std::max(num_tiles, 1));
   if (static_cast<int>(plan.size()) > kMaxLaunches)
     return fail(SA_ERR_CAPACITY, "batch needs %zu scan launches (max %d)", plan.size(), kMaxLaunches);
+  const int mode = e->opt_profile ? sa::kModeProf : sa::kModeProd;
+  const float eps_rel = scan_eps_rel(e->dim);
 
   // The candidate lists, shared thresholds and drift counters are one set of scratch buffers: a search issued on
   // another stream than the previous one must not start before that one has finished with them.
   SA_CUDA(cudaStreamWaitEvent(st, e->scratch_free, 0));
+  if (e->scratch_dirty) {
+    int rc = zero_scan_scratch(e, st);
+    if (rc) return rc;
+    e->scratch_dirty = false;
+  }
   sa_engine::Timing& tm = e->ring[e->n_searches % kTimingRing];
   tm.launches = 0;
   tm.kernels = 0;
   SA_CUDA(cudaEventRecord(tm.ev_total[0], st));
+  e->scratch_dirty = true;  // cleared again once the fixup kernel (which re-zeroes the scratch) is enqueued
+  int min_tl = sa::kMaxLanes;
   for (size_t li = 0; li < plan.size(); ++li) {
     const LaunchPlan& lp = plan[li];
     const uint16_t* qptr = q_bf16 + static_cast<size_t>(lp.q0) * e->dim;
@@ -316,43 +365,38 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
     sp.tl_count = lp.tl;
     sp.part_score = e->part_score;
     sp.part_idx = e->part_idx;
+    sp.part_drop = e->part_drop;
     sp.corpus_evict_first = (lp.nqb == 1) ? 1 : 0;  // a tile nobody else will ask for: stream it through L2
     sp.lane_progress = nullptr;
-    sp.max_drift = std::max(e->opt_max_drift, 0);
+    sp.max_drift = e->opt_max_drift >= 0 ? e->opt_max_drift : 1;
     sp.pace_gain = 0;
-    sp.pace_max = e->opt_pace_max;
     sp.unit_map = e->opt_unit_map;
     // drift-control defaults from the sweeps in tools/gpu_l2exp.sh (DRAM bytes vs time): pairs 16 cycles per tile of
-    // lead beyond 1 tile, single CTAs 32; with two passes per tile (qpu 2) a tile of lead is twice as long, so pace
-    // from the first tile of lead and twice as hard
-    const int gain = e->opt_pace_gain >= 0 ? e->opt_pace_gain : ((lp.cg == 2 && lp.qpu == 1) ? 16 : 32);
+    // lead beyond 1 tile, single CTAs 32
+    const int gain = e->opt_pace_gain >= 0 ? e->opt_pace_gain : (lp.cg == 2 ? 16 : 32);
     sp.pace_max = e->opt_pace_max >= 0 ? e->opt_pace_max : 8 * gain;
-    if (e->opt_max_drift < 0) sp.max_drift = lp.qpu == 2 ? 0 : 1;
-    const int nslots = (lp.nqb + lp.qpu - 1) / lp.qpu;  // units per tile lane
-    if (nslots > 1 && gain > 0) {
-      sp.lane_progress = e->lane_progress;
+    if (lp.nqb > 1 && gain > 0) {
+      sp.lane_progress = e->lane_progress + li * e->num_sms;  // this launch's slice (zero: see sa_engine)
       sp.pace_gain = gain;
-      SA_CUDA(cudaMemsetAsync(e->lane_progress, 0, sizeof(int) * nslots * lp.tl, st));
     }
-    sp.thr_shared = nullptr;
-    if (e->opt_share_thresholds && lp.tl > 1) {
-      sp.thr_shared = e->thr_shared;
-      SA_CUDA(cudaMemsetAsync(e->thr_shared, 0, sizeof(unsigned) * lp.nqb * 128 * lp.cg, st));
-    }
+    sp.thr_shared = (e->opt_share_thresholds && lp.tl > 1) ? e->thr_shared + lp.q0 : nullptr;
     sp.dbg_dots = nullptr;
     sp.dbg_tile = -1;
     sp.dbg_times = e->opt_record_times ? e->dbg_times : nullptr;
-    const int grid = nslots * lp.tl * lp.cg;
+    sp.prof = e->prof;
+    const int grid = lp.nqb * lp.tl * lp.cg;
     e->last_grid = grid;
+    min_tl = std::min(min_tl, lp.tl);
 
     SA_CUDA(cudaEventRecord(tm.ev_scan[li][0], st));
-    rc = launch_scan_dispatch(lp.cg, kl, lp.qpu, false, tq, e->tmap_c[lp.cg - 1], sp, grid, st);
+    rc = launch_scan_dispatch(lp.cg, kl, mode, tq, e->tmap_c[lp.cg - 1], sp, grid, st);
     if (rc) return rc;
     SA_CUDA(cudaEventRecord(tm.ev_scan[li][1], st));
 
     sa::MergeParams mp = {};
     mp.part_score = e->part_score;
     mp.part_idx = e->part_idx;
+    mp.part_drop = e->part_drop;
     mp.corpus = e->corpus;
     mp.queries = qptr;
     mp.dim = e->dim;
@@ -361,11 +405,15 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
     mp.cg = lp.cg;
     mp.nqb = lp.nqb;
     mp.tl_count = lp.tl;
-    mp.qpu = lp.qpu;
     mp.unit_map = e->opt_unit_map;
-    mp.out_score = out_score + static_cast<size_t>(lp.q0) * k;
-    mp.out_idx = out_idx + static_cast<size_t>(lp.q0) * k;
-    mp.out_score64 = out_score64 ? out_score64 + static_cast<size_t>(lp.q0) * k : nullptr;
+    mp.q0 = lp.q0;
+    mp.eps_rel = eps_rel;
+    mp.res64 = e->res64 + static_cast<size_t>(lp.q0) * k;
+    mp.residx = e->residx + static_cast<size_t>(lp.q0) * k;
+    mp.fix_entries = e->fix_entries;
+    mp.fix_count = e->fix_counters;
+    mp.fix_query = e->fix_query;
+    mp.force_fix = e->opt_force_fix;
     if (kl == 16)
       sa::sa_merge_rescore_kernel<16><<<lp.nq, sa::kMergeThreads, 0, st>>>(mp);
     else
@@ -373,6 +421,48 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
     SA_CUDA(cudaGetLastError());
     tm.launches += 1;
     tm.kernels += 2;
+  }
+  if (e->opt_count_fix) {
+    int cnt = 0;
+    SA_CUDA(cudaMemcpyAsync(&cnt, e->fix_counters, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SA_CUDA(cudaStreamSynchronize(st));
+    e->last_fix_entries = cnt;
+  }
+  {
+    sa::FixParams fp = {};
+    fp.entries = e->fix_entries;
+    fp.fix_count = e->fix_counters;
+    fp.done_count = e->fix_counters + 1;
+    fp.fix_query = e->fix_query;
+    fp.corpus = e->corpus;
+    fp.inv_norm = e->inv_norm;
+    fp.queries = q_bf16;
+    fp.n_rows = n_rows;
+    fp.num_tiles = num_tiles;
+    fp.dim = e->dim;
+    fp.nq = nq;
+    fp.k = k;
+    const int tiles_per_lane = (std::max(num_tiles, 1) + min_tl - 1) / min_tl;
+    fp.chunks_per_entry = (tiles_per_lane + sa::kFixChunkTiles - 1) / sa::kFixChunkTiles;
+    fp.eps_rel = eps_rel;
+    fp.res64 = e->res64;
+    fp.residx = e->residx;
+    fp.out_score = out_score;
+    fp.out_idx = out_idx;
+    fp.out_score64 = out_score64;
+    fp.out_packed = out_packed;
+    fp.row_offset = row_offset;
+    fp.zero_a = e->thr_shared;
+    fp.zero_a_n = std::min(e->thr_n, ((nq + 255) / 256) * 256);
+    fp.zero_b = e->lane_progress;
+    fp.zero_b_n = static_cast<int>(plan.size()) * e->num_sms;
+    const size_t smem = static_cast<size_t>(e->dim) * sizeof(float);
+    if (smem > 48 * 1024)
+      SA_CUDA(cudaFuncSetAttribute(sa::sa_fixup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    sa::sa_fixup_kernel<<<2 * e->num_sms, sa::kFixThreads, smem, st>>>(fp);
+    SA_CUDA(cudaGetLastError());
+    tm.kernels += 1;
+    e->scratch_dirty = false;
   }
   SA_CUDA(cudaEventRecord(tm.ev_total[1], st));
   SA_CUDA(cudaEventRecord(e->scratch_free, st));
@@ -387,30 +477,31 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
 }  // namespace
 
 namespace {
+// The epilogue's rule fed chunk by chunk exactly as the kernel feeds it: 32 scores per chunk (the tail chunk padded with
+// NaN = masked rows), a shared bound becoming visible at a chunk boundary (the kernel applies it per accumulator).
 template <int kKL>
-void run_list(const float* score, const int32_t* row, int n, const float* floor_after, float* out_sc, int32_t* out_id) {
-  // The epilogue's per-value rule, value by value: insert when s > max(own kKL-th best, shared floor).
-  float sc[kKL];
-  int id[kKL];
-  for (int i = 0; i < kKL; ++i) {
-    sc[i] = -INFINITY;
-    id[i] = -1;
-  }
-  float thr_floor = -INFINITY, thr = -INFINITY;
-  for (int i = 0; i < n; ++i) {
-    if (floor_after && floor_after[i] > -INFINITY) {  // a bound published by another tile lane becomes visible
-      thr_floor = sa::float_below(floor_after[i]);
-      thr = fmaxf(thr, thr_floor);
+void run_list(const float* score, const int32_t* row, int n, const float* floor_after, float* out_sc, int32_t* out_id,
+              float* out_drop) {
+  sa::TopList<kKL> L;
+  L.init(nullptr);
+  float ones[sa::kChunk];
+  for (int j = 0; j < sa::kChunk; ++j) ones[j] = 1.0f;
+  for (int c0 = 0; c0 < n; c0 += sa::kChunk) {
+    float v[sa::kChunk];
+    for (int j = 0; j < sa::kChunk; ++j) {
+      const int i = c0 + j;
+      v[j] = i < n ? score[i] : NAN;
+      if (i < n && floor_after && floor_after[i] > -INFINITY) L.apply_shared(sa::float_to_key(floor_after[i]));
     }
-    if (score[i] > thr) {
-      sa::list_insert<kKL>(sc, id, score[i], row[i]);
-      thr = fmaxf(sc[kKL - 1], thr_floor);
-    }
+    // rows of a chunk are consecutive in the kernel; the hook accepts arbitrary row ids, so the list records positions
+    // (c0 + j) and they are translated through row[] at the end
+    sa::chunk_process<kKL>(L, v, ones, c0);
   }
   for (int i = 0; i < kKL; ++i) {
-    out_sc[i] = sc[i];
-    out_id[i] = id[i];
+    out_sc[i] = L.sc[i];
+    out_id[i] = L.id[i] >= 0 ? row[L.id[i]] : -1;
   }
+  if (out_drop) *out_drop = L.drop;
 }
 }  // namespace
 
@@ -473,23 +564,39 @@ int sa_engine_create(sa_engine** out, int device, int dim, int64_t capacity_rows
   } while (0)
   SA_TRY(cudaMalloc(&e->part_score, part_elems * sizeof(float)));
   SA_TRY(cudaMalloc(&e->part_idx, part_elems * sizeof(int)));
+  SA_TRY(cudaMalloc(&e->part_drop, static_cast<size_t>(e->num_sms) * 128 * sizeof(float)));
+  SA_TRY(cudaMalloc(&e->res64, relems * sizeof(double)));
+  SA_TRY(cudaMalloc(&e->residx, relems * sizeof(int)));
+  SA_TRY(cudaMalloc(&e->fix_entries, static_cast<size_t>(kMaxLaunches) * e->num_sms * 128 * sizeof(sa::FixEntry)));
+  SA_TRY(cudaMalloc(&e->fix_query, static_cast<size_t>(max_batch) * sizeof(sa::FixQuery)));
+  SA_TRY(cudaMalloc(&e->fix_counters, 2 * sizeof(int)));
+  SA_TRY(cudaMalloc(&e->prof, static_cast<size_t>(e->num_sms) * sizeof(sa::ScanProf)));
+  SA_TRY(cudaMemset(e->prof, 0, static_cast<size_t>(e->num_sms) * sizeof(sa::ScanProf)));
   SA_TRY(cudaMalloc(&e->q_bf16, qelems * 2));
   SA_TRY(cudaMalloc(&e->q_f32, qelems * 4));
   SA_TRY(cudaMalloc(&e->res_score, relems * 4));
   SA_TRY(cudaMalloc(&e->res_idx, relems * 4));
+  SA_TRY(cudaMalloc(&e->hits, relems * sizeof(sa::PackedHit)));
+  SA_TRY(cudaMalloc(&e->res_row64, relems * sizeof(long long)));
   SA_TRY(cudaMalloc(&e->d_stage, static_cast<size_t>(e->stage_rows) * dim * 4));
   for (int i = 0; i <= kHostSlots; ++i) {
     SA_TRY(cudaHostAlloc(&e->slot[i].h_q, qelems * 4, cudaHostAllocDefault));
     SA_TRY(cudaHostAlloc(&e->slot[i].h_score, relems * 4, cudaHostAllocDefault));
     SA_TRY(cudaHostAlloc(&e->slot[i].h_idx, relems * 4, cudaHostAllocDefault));
+    SA_TRY(cudaHostAlloc(&e->slot[i].h_row64, relems * sizeof(long long), cudaHostAllocDefault));
     SA_TRY(cudaEventCreateWithFlags(&e->slot[i].done, cudaEventDisableTiming));
   }
   SA_TRY(cudaHostAlloc(&e->h_stage, static_cast<size_t>(e->stage_rows) * dim * 4, cudaHostAllocDefault));
   // a blocking stream: ordered after work already queued on the legacy default stream (torch's default)
   SA_TRY(cudaStreamCreate(&e->own_stream));
   SA_TRY(cudaEventCreateWithFlags(&e->scratch_free, cudaEventDisableTiming));
-  SA_TRY(cudaMalloc(&e->lane_progress, sizeof(int) * e->num_sms));
-  SA_TRY(cudaMalloc(&e->thr_shared, sizeof(unsigned) * e->num_sms * 128));
+  e->thr_n = ((max_batch + 255) / 256) * 256 + 256;
+  SA_TRY(cudaMalloc(&e->lane_progress, sizeof(int) * kMaxLaunches * e->num_sms));
+  SA_TRY(cudaMalloc(&e->thr_shared, sizeof(unsigned) * e->thr_n));
+  SA_TRY(cudaMemset(e->lane_progress, 0, sizeof(int) * kMaxLaunches * e->num_sms));
+  SA_TRY(cudaMemset(e->thr_shared, 0, sizeof(unsigned) * e->thr_n));
+  SA_TRY(cudaMemset(e->fix_counters, 0, 2 * sizeof(int)));
+  SA_TRY(cudaMemset(e->fix_query, 0, static_cast<size_t>(max_batch) * sizeof(sa::FixQuery)));
   SA_TRY(cudaMalloc(&e->dbg_times, sizeof(long long) * 2 * e->num_sms));
   for (int r = 0; r < kTimingRing; ++r)
     for (int i = 0; i < kMaxLaunches; ++i) e->ring[r].ev_scan[i][0] = e->ring[r].ev_scan[i][1] = nullptr;
@@ -512,15 +619,25 @@ void sa_engine_destroy(sa_engine* e) {
   cudaDeviceSynchronize();
   cudaFree(e->part_score);
   cudaFree(e->part_idx);
+  cudaFree(e->part_drop);
+  cudaFree(e->res64);
+  cudaFree(e->residx);
+  cudaFree(e->fix_entries);
+  cudaFree(e->fix_query);
+  cudaFree(e->fix_counters);
+  cudaFree(e->prof);
   cudaFree(e->q_bf16);
   cudaFree(e->q_f32);
   cudaFree(e->res_score);
   cudaFree(e->res_idx);
+  cudaFree(e->hits);
+  cudaFree(e->res_row64);
   cudaFree(e->d_stage);
   for (int i = 0; i <= kHostSlots; ++i) {
     cudaFreeHost(e->slot[i].h_q);
     cudaFreeHost(e->slot[i].h_score);
     cudaFreeHost(e->slot[i].h_idx);
+    cudaFreeHost(e->slot[i].h_row64);
     if (e->slot[i].done) cudaEventDestroy(e->slot[i].done);
   }
   cudaFreeHost(e->h_stage);
@@ -542,8 +659,9 @@ void sa_engine_destroy(sa_engine* e) {
 int sa_corpus_bind(sa_engine* e, void* rows_bf16_dev, float* inv_norm_dev, int64_t n_valid) {
   if (!e || !rows_bf16_dev || !inv_norm_dev) return fail(SA_ERR_ARG, "null argument");
   if (reinterpret_cast<uintptr_t>(rows_bf16_dev) % 16) return fail(SA_ERR_ARG, "corpus must be 16-byte aligned");
+  if (reinterpret_cast<uintptr_t>(inv_norm_dev) % 16) return fail(SA_ERR_ARG, "inv_norm must be 16-byte aligned");
   if (n_valid < 0 || n_valid > e->capacity) return fail(SA_ERR_CAPACITY, "n_valid outside [0, capacity]");
-  SA_CUDA(cudaSetDevice(e->device));
+  SA_ON_DEVICE(e->device);
   int rc = encode_rows_map(&e->tmap_c[0], rows_bf16_dev, static_cast<uint64_t>(e->capacity), e->dim, sa::kBlockN);
   if (rc) return rc;
   rc = encode_rows_map(&e->tmap_c[1], rows_bf16_dev, static_cast<uint64_t>(e->capacity), e->dim, sa::kBlockN / 2);
@@ -561,7 +679,7 @@ int sa_corpus_commit(sa_engine* e, int64_t first_row, int64_t n_new, uintptr_t s
   if (first_row != e->n_rows) return fail(SA_ERR_ARG, "commit must start at the current row count %lld", (long long)e->n_rows);
   if (n_new < 0 || first_row + n_new > e->capacity) return fail(SA_ERR_CAPACITY, "commit past capacity");
   if (n_new == 0) return SA_OK;
-  SA_CUDA(cudaSetDevice(e->device));
+  SA_ON_DEVICE(e->device);
   const long long threads = n_new * 32;
   const int block = 256;
   const long long grid = (threads + block - 1) / block;
@@ -578,7 +696,7 @@ int sa_corpus_append_f32(sa_engine* e, const float* rows_f32_dev, int64_t n_new,
   if (!rows_f32_dev) return fail(SA_ERR_ARG, "null rows");
   if (n_new < 0 || e->n_rows + n_new > e->capacity) return fail(SA_ERR_CAPACITY, "append past capacity");
   if (n_new == 0) return SA_OK;
-  SA_CUDA(cudaSetDevice(e->device));
+  SA_ON_DEVICE(e->device);
   const long long threads = n_new * 32;
   const int block = 256;
   const long long grid = (threads + block - 1) / block;
@@ -594,7 +712,7 @@ int sa_corpus_append_host_f32(sa_engine* e, const float* rows_f32_host, int64_t 
   if (rc) return rc;
   if (!rows_f32_host) return fail(SA_ERR_ARG, "null rows");
   if (n_new < 0 || e->n_rows + n_new > e->capacity) return fail(SA_ERR_CAPACITY, "append past capacity");
-  SA_CUDA(cudaSetDevice(e->device));
+  SA_ON_DEVICE(e->device);
   int64_t done = 0;
   while (done < n_new) {
     const int64_t n = std::min(e->stage_rows, n_new - done);
@@ -622,7 +740,7 @@ int sa_search(sa_engine* e, const void* q_bf16_dev, int nq, int k, float* out_sc
   int rc = check_engine(e);
   if (rc) return rc;
   return do_search(e, static_cast<const uint16_t*>(q_bf16_dev), nq, k, out_score_dev, out_idx_dev, out_score64_dev,
-                   reinterpret_cast<cudaStream_t>(stream));
+                   nullptr, 0, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int sa_search_f32(sa_engine* e, const float* q_f32_dev, int nq, int k, float* out_score_dev, int32_t* out_idx_dev,
@@ -631,58 +749,211 @@ int sa_search_f32(sa_engine* e, const float* q_f32_dev, int nq, int k, float* ou
   if (rc) return rc;
   if (!q_f32_dev) return fail(SA_ERR_ARG, "null queries");
   if (nq <= 0 || nq > e->max_batch) return fail(SA_ERR_CAPACITY, "nq %d outside [1, max_batch %d]", nq, e->max_batch);
-  SA_CUDA(cudaSetDevice(e->device));
+  SA_ON_DEVICE(e->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   SA_CUDA(cudaStreamWaitEvent(st, e->scratch_free, 0));  // q_bf16 is scratch too: the previous search still reads it
   const long long threads = static_cast<long long>(nq) * 32;
   sa::sa_convert_rows_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(q_f32_dev, e->q_bf16,
                                                                                          nullptr, nq, e->dim);
   SA_CUDA(cudaGetLastError());
-  rc = do_search(e, e->q_bf16, nq, k, out_score_dev, out_idx_dev, out_score64_dev, st);
+  rc = do_search(e, e->q_bf16, nq, k, out_score_dev, out_idx_dev, out_score64_dev, nullptr, 0, st);
   if (rc == SA_OK) e->ring[(e->n_searches - 1) % kTimingRing].kernels += 1;
   return rc;
 }
 
 namespace {
+// ------------------------------------------------------------------------------------------------------------------
+// Multi-GPU exchange: every rank scans its row shard, ONE all-gather of the packed per-query
+// (cosine f64, global row) lists -- nq*k*16 bytes per rank -- and a k-way merge on every rank.  NCCL is loaded at run
+// time: the copy already in the process if there is one (torch's), else SA_NCCL_LIB / sa_comm_set_library, else the
+// system libnccl.so.2 -- so exactly one NCCL ever lives in the process.
+// ------------------------------------------------------------------------------------------------------------------
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetVersion)(int*) = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string path;
+};
+NcclApi g_nccl;
+std::string g_nccl_path_hint;
 
-int host_submit(sa_engine* e, int si, const float* q_f32_host, int nq, int k) {
-  sa_engine::HostSlot& sl = e->slot[si];
-  if (sl.busy) return fail(SA_ERR_ARG, "host slot %d still holds an unwaited search", si);
-  if (!q_f32_host) return fail(SA_ERR_ARG, "null buffer");
-  if (nq <= 0 || nq > e->max_batch) return fail(SA_ERR_CAPACITY, "nq %d outside [1, max_batch %d]", nq, e->max_batch);
-  if (k <= 0 || k > e->max_k) return fail(SA_ERR_ARG, "k %d outside [1, max_k %d]", k, e->max_k);
-  SA_CUDA(cudaSetDevice(e->device));
-  const size_t qbytes = static_cast<size_t>(nq) * e->dim * 4;
-  const size_t rbytes = static_cast<size_t>(nq) * k * 4;
-  // A query buffer that is already page-locked (sa_host_alloc, cudaHostRegister, torch pin_memory) is DMA'd
-  // directly -- the caller then keeps it unchanged until the matching wait; pageable memory is staged.
-  const float* q_src = q_f32_host;
-  if (!is_pinned(q_f32_host)) {
-    memcpy(sl.h_q, q_f32_host, qbytes);
-    q_src = sl.h_q;
+int load_nccl() {
+  if (g_nccl.handle) return SA_OK;
+  std::vector<std::string> tried;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);  // already in the process (torch imported)?
+  std::string from = "already loaded libnccl.so.2";
+  auto try_path = [&](const std::string& pth) {
+    if (h || pth.empty()) return;
+    h = dlopen(pth.c_str(), RTLD_NOW | RTLD_GLOBAL);
+    if (h) from = pth;
+    else tried.push_back(pth);
+  };
+  try_path(g_nccl_path_hint);
+  if (const char* env = getenv("SA_NCCL_LIB")) try_path(env);
+  try_path("libnccl.so.2");
+  try_path("libnccl.so");
+  if (!h) {
+    std::string msg;
+    for (auto& t : tried) msg += " " + t;
+    return fail(SA_ERR_COMM, "NCCL not found (tried:%s); set SA_NCCL_LIB or call sa_comm_set_library", msg.c_str());
   }
-  SA_CUDA(cudaMemcpyAsync(e->q_f32, q_src, qbytes, cudaMemcpyHostToDevice, e->own_stream));
-  int rc = sa_search_f32(e, e->q_f32, nq, k, e->res_score, e->res_idx, nullptr,
-                         reinterpret_cast<uintptr_t>(e->own_stream));
-  if (rc) return rc;
-  SA_CUDA(cudaMemcpyAsync(sl.h_score, e->res_score, rbytes, cudaMemcpyDeviceToHost, e->own_stream));
-  SA_CUDA(cudaMemcpyAsync(sl.h_idx, e->res_idx, rbytes, cudaMemcpyDeviceToHost, e->own_stream));
-  SA_CUDA(cudaEventRecord(sl.done, e->own_stream));
-  sl.nq = nq;
-  sl.k = k;
-  sl.busy = true;
+#define SA_NCCL_SYM(field, name)                                                          \
+  g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(h, name));                \
+  if (!g_nccl.field) return fail(SA_ERR_COMM, "%s lacks symbol %s", from.c_str(), name)
+  SA_NCCL_SYM(GetVersion, "ncclGetVersion");
+  SA_NCCL_SYM(GetUniqueId, "ncclGetUniqueId");
+  SA_NCCL_SYM(CommInitRank, "ncclCommInitRank");
+  SA_NCCL_SYM(CommInitAll, "ncclCommInitAll");
+  SA_NCCL_SYM(CommDestroy, "ncclCommDestroy");
+  SA_NCCL_SYM(AllGather, "ncclAllGather");
+  SA_NCCL_SYM(GroupStart, "ncclGroupStart");
+  SA_NCCL_SYM(GroupEnd, "ncclGroupEnd");
+  SA_NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef SA_NCCL_SYM
+  g_nccl.handle = h;
+  g_nccl.path = from;
   return SA_OK;
 }
 
-int host_wait(sa_engine* e, int si, float* out_score_host, int32_t* out_idx_host) {
+#define SA_NCCL(call)                                                                                          \
+  do {                                                                                                         \
+    ncclResult_t _r = (call);                                                                                  \
+    if (_r != ncclSuccess)                                                                                     \
+      return fail(SA_ERR_COMM, "%s failed: %s (%s:%d)", #call, g_nccl.GetErrorString(_r), __FILE__, __LINE__); \
+  } while (0)
+
+}  // namespace
+
+struct sa_comm {
+  int n_ranks = 0;
+  int rank = -1;                    // >= 0: one rank of a multi-process communicator; -1: single process, all ranks here
+  std::vector<int> devices;         // device of each local rank
+  std::vector<ncclComm_t> comms;    // one per local rank
+  std::vector<sa::PackedHit*> gathered;  // per local rank: [n_ranks][cap_nq][cap_k], grown on demand
+  std::vector<size_t> gathered_elems;
+};
+
+namespace {
+
+int comm_gather_buffer(sa_comm* c, int local, int nq, int k, sa::PackedHit** out) {
+  const size_t need = static_cast<size_t>(c->n_ranks) * nq * k;
+  if (c->gathered_elems[local] < need) {
+    DeviceGuard g(c->devices[local]);
+    if (c->gathered[local]) {
+      cudaDeviceSynchronize();  // growth is rare (first call, or a larger batch than ever before)
+      cudaFree(c->gathered[local]);
+      c->gathered[local] = nullptr;
+      c->gathered_elems[local] = 0;
+    }
+    SA_CUDA(cudaMalloc(&c->gathered[local], need * sizeof(sa::PackedHit)));
+    c->gathered_elems[local] = need;
+  }
+  *out = c->gathered[local];
+  return SA_OK;
+}
+
+// This rank's part of a sharded search on stream st: shard scan -> packed hits -> all-gather -> merge.  `phases` selects
+// the steps (bit 0 scan, bit 1 all-gather, bit 2 merge) so a single process driving several GPUs can put the collectives
+// of all its ranks into one NCCL group (inside a group the collective is only enqueued at ncclGroupEnd, so nothing that
+// must follow it on the stream may be issued before the group closes).
+int sharded_search_on_stream(sa_comm* c, int local, sa_engine* e, const uint16_t* q_bf16, int nq, int k,
+                             int64_t row_offset, float* out_score_dev, long long* out_row_dev, cudaStream_t st,
+                             int phases = 7) {
+  int rc;
+  if (phases & 1) {
+    rc = do_search(e, q_bf16, nq, k, e->res_score, e->res_idx, nullptr, e->hits, row_offset, st);
+    if (rc) return rc;
+  }
+  sa::PackedHit* gathered = nullptr;
+  rc = comm_gather_buffer(c, local, nq, k, &gathered);
+  if (rc) return rc;
+  if (phases & 2) {
+    const size_t bytes = static_cast<size_t>(nq) * k * sizeof(sa::PackedHit);
+    SA_NCCL(g_nccl.AllGather(e->hits, gathered, bytes, ncclChar, c->comms[local], st));
+  }
+  if (phases & 4) {
+    sa::sa_merge_packed_kernel<<<(nq + 127) / 128, 128, 0, st>>>(gathered, c->n_ranks, nq, k, out_score_dev, out_row_dev);
+    SA_CUDA(cudaGetLastError());
+    e->ring[(e->n_searches - 1) % kTimingRing].kernels += 2;  // the collective and the shard merge
+  }
+  return SA_OK;
+}
+
+int convert_queries(sa_engine* e, const float* q_f32_dev, int nq, cudaStream_t st) {
+  SA_CUDA(cudaStreamWaitEvent(st, e->scratch_free, 0));  // q_bf16 is scratch too: the previous search still reads it
+  const long long threads = static_cast<long long>(nq) * 32;
+  sa::sa_convert_rows_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(q_f32_dev, e->q_bf16, nullptr,
+                                                                                         nq, e->dim);
+  SA_CUDA(cudaGetLastError());
+  return SA_OK;
+}
+
+// Host-buffer search into slot si.  comm == nullptr: this engine alone (shard-local int32 rows); otherwise this rank's
+// part of a sharded search (global int64 rows, identical on every rank).  `phases` as in sharded_search_on_stream
+// (bit 0 also covers the H2D copy and the conversion, bit 2 the D2H copies and the slot's event).
+int host_submit(sa_engine* e, int si, const float* q_f32_host, int nq, int k, sa_comm* c, int local, int64_t row_offset,
+                int phases = 7) {
+  sa_engine::HostSlot& sl = e->slot[si];
+  SA_ON_DEVICE(e->device);
+  cudaStream_t st = e->own_stream;
+  const size_t rbytes = static_cast<size_t>(nq) * k * 4;
+  if (phases & 1) {
+    if (sl.busy) return fail(SA_ERR_ARG, "host slot %d still holds an unwaited search", si);
+    if (!q_f32_host) return fail(SA_ERR_ARG, "null buffer");
+    if (nq <= 0 || nq > e->max_batch) return fail(SA_ERR_CAPACITY, "nq %d outside [1, max_batch %d]", nq, e->max_batch);
+    if (k <= 0 || k > e->max_k) return fail(SA_ERR_ARG, "k %d outside [1, max_k %d]", k, e->max_k);
+    const size_t qbytes = static_cast<size_t>(nq) * e->dim * 4;
+    // A query buffer that is already page-locked (sa_host_alloc, cudaHostRegister, torch pin_memory) is DMA'd
+    // directly -- the caller then keeps it unchanged until the matching wait; pageable memory is staged.
+    const float* q_src = q_f32_host;
+    if (!is_pinned(q_f32_host)) {
+      memcpy(sl.h_q, q_f32_host, qbytes);
+      q_src = sl.h_q;
+    }
+    SA_CUDA(cudaMemcpyAsync(e->q_f32, q_src, qbytes, cudaMemcpyHostToDevice, st));
+    int rc = convert_queries(e, e->q_f32, nq, st);
+    if (rc) return rc;
+    if (c == nullptr) {
+      rc = do_search(e, e->q_bf16, nq, k, e->res_score, e->res_idx, nullptr, nullptr, 0, st);
+      if (rc) return rc;
+    }
+  }
+  if (c != nullptr) {
+    int rc = sharded_search_on_stream(c, local, e, e->q_bf16, nq, k, row_offset, e->res_score, e->res_row64, st, phases);
+    if (rc) return rc;
+  }
+  if (phases & 4) {
+    SA_CUDA(cudaMemcpyAsync(sl.h_score, e->res_score, rbytes, cudaMemcpyDeviceToHost, st));
+    if (c == nullptr) SA_CUDA(cudaMemcpyAsync(sl.h_idx, e->res_idx, rbytes, cudaMemcpyDeviceToHost, st));
+    else SA_CUDA(cudaMemcpyAsync(sl.h_row64, e->res_row64, 2 * rbytes, cudaMemcpyDeviceToHost, st));
+    e->ring[(e->n_searches - 1) % kTimingRing].kernels += 1;  // the fp32 -> bf16 conversion
+    SA_CUDA(cudaEventRecord(sl.done, st));
+    sl.nq = nq;
+    sl.k = k;
+    sl.sharded = c != nullptr;
+    sl.busy = true;
+  }
+  return SA_OK;
+}
+
+int host_wait(sa_engine* e, int si, float* out_score_host, void* out_idx_host, bool sharded) {
   sa_engine::HostSlot& sl = e->slot[si];
   if (!sl.busy) return fail(SA_ERR_ARG, "host slot %d has no search in flight", si);
+  if (sl.sharded != sharded) return fail(SA_ERR_ARG, "host slot %d holds a %s search", si, sl.sharded ? "sharded" : "local");
   if (!out_score_host || !out_idx_host) return fail(SA_ERR_ARG, "null buffer");
-  SA_CUDA(cudaSetDevice(e->device));
+  SA_ON_DEVICE(e->device);
   SA_CUDA(cudaEventSynchronize(sl.done));
   const size_t rbytes = static_cast<size_t>(sl.nq) * sl.k * 4;
   memcpy(out_score_host, sl.h_score, rbytes);
-  memcpy(out_idx_host, sl.h_idx, rbytes);
+  if (sharded) memcpy(out_idx_host, sl.h_row64, 2 * rbytes);
+  else memcpy(out_idx_host, sl.h_idx, rbytes);
   sl.busy = false;
   return SA_OK;
 }
@@ -695,23 +966,23 @@ int sa_search_host(sa_engine* e, const float* q_f32_host, int nq, int k, float* 
   if (rc) return rc;
   if (!out_score_host || !out_idx_host) return fail(SA_ERR_ARG, "null buffer");
   e->slot[kHostSlots].busy = false;  // the private slot of the blocking call
-  rc = host_submit(e, kHostSlots, q_f32_host, nq, k);
+  rc = host_submit(e, kHostSlots, q_f32_host, nq, k, nullptr, 0, 0);
   if (rc) return rc;
-  return host_wait(e, kHostSlots, out_score_host, out_idx_host);
+  return host_wait(e, kHostSlots, out_score_host, out_idx_host, false);
 }
 
 int sa_search_host_submit(sa_engine* e, int slot, const float* q_f32_host, int nq, int k) {
   int rc = check_engine(e);
   if (rc) return rc;
   if (slot < 0 || slot >= kHostSlots) return fail(SA_ERR_ARG, "slot %d outside [0, %d)", slot, kHostSlots);
-  return host_submit(e, slot, q_f32_host, nq, k);
+  return host_submit(e, slot, q_f32_host, nq, k, nullptr, 0, 0);
 }
 
 int sa_search_host_wait(sa_engine* e, int slot, float* out_score_host, int32_t* out_idx_host) {
   int rc = check_engine(e);
   if (rc) return rc;
   if (slot < 0 || slot >= kHostSlots) return fail(SA_ERR_ARG, "slot %d outside [0, %d)", slot, kHostSlots);
-  return host_wait(e, slot, out_score_host, out_idx_host);
+  return host_wait(e, slot, out_score_host, out_idx_host, false);
 }
 
 int sa_merge_shards(sa_engine* e, const double* score64_dev, const int64_t* global_idx_dev, int n_shards, int nq,
@@ -719,12 +990,219 @@ int sa_merge_shards(sa_engine* e, const double* score64_dev, const int64_t* glob
   if (!e || !score64_dev || !global_idx_dev || !out_score_dev || !out_idx_dev) return fail(SA_ERR_ARG, "null argument");
   if (n_shards <= 0 || n_shards > 64) return fail(SA_ERR_ARG, "n_shards %d outside [1, 64]", n_shards);
   if (nq <= 0 || k <= 0) return fail(SA_ERR_ARG, "nq and k must be positive");
-  SA_CUDA(cudaSetDevice(e->device));
+  SA_ON_DEVICE(e->device);
   sa::sa_merge_shards_kernel<<<(nq + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       score64_dev, reinterpret_cast<const long long*>(global_idx_dev), n_shards, nq, k, out_score_dev,
       reinterpret_cast<long long*>(out_idx_dev));
   SA_CUDA(cudaGetLastError());
   return SA_OK;
+}
+
+int sa_search_hits(sa_engine* e, const void* q_bf16_dev, int nq, int k, int64_t row_offset, sa_hit* out_hits_dev,
+                   uintptr_t stream) {
+  int rc = check_engine(e);
+  if (rc) return rc;
+  if (!out_hits_dev) return fail(SA_ERR_ARG, "null buffer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  {
+    SA_ON_DEVICE(e->device);
+    SA_CUDA(cudaStreamWaitEvent(st, e->scratch_free, 0));  // res_score / res_idx below are engine scratch
+  }
+  return do_search(e, static_cast<const uint16_t*>(q_bf16_dev), nq, k, e->res_score, e->res_idx, nullptr,
+                   reinterpret_cast<sa::PackedHit*>(out_hits_dev), row_offset, st);
+}
+
+int sa_merge_hits(sa_engine* e, const sa_hit* hits_dev, int n_shards, int nq, int k, float* out_score_dev,
+                  int64_t* out_row_dev, uintptr_t stream) {
+  if (!e || !hits_dev || !out_score_dev || !out_row_dev) return fail(SA_ERR_ARG, "null argument");
+  if (n_shards <= 0 || n_shards > 64) return fail(SA_ERR_ARG, "n_shards %d outside [1, 64]", n_shards);
+  if (nq <= 0 || k <= 0) return fail(SA_ERR_ARG, "nq and k must be positive");
+  SA_ON_DEVICE(e->device);
+  sa::sa_merge_packed_kernel<<<(nq + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const sa::PackedHit*>(hits_dev), n_shards, nq, k, out_score_dev,
+      reinterpret_cast<long long*>(out_row_dev));
+  SA_CUDA(cudaGetLastError());
+  return SA_OK;
+}
+
+// ---- communicator ---------------------------------------------------------------------------------------------------
+int sa_comm_set_library(const char* path) {
+  g_nccl_path_hint = path ? path : "";
+  return SA_OK;
+}
+
+int sa_comm_nccl_version(int* version, char* path_out, int path_cap) {
+  int rc = load_nccl();
+  if (rc) return rc;
+  if (version) SA_NCCL(g_nccl.GetVersion(version));
+  if (path_out && path_cap > 0) snprintf(path_out, path_cap, "%s", g_nccl.path.c_str());
+  return SA_OK;
+}
+
+int sa_comm_unique_id(void* id_out_128) {
+  if (!id_out_128) return fail(SA_ERR_ARG, "null id");
+  int rc = load_nccl();
+  if (rc) return rc;
+  static_assert(sizeof(ncclUniqueId) == SA_COMM_ID_BYTES, "SA_COMM_ID_BYTES must match ncclUniqueId");
+  ncclUniqueId id;
+  SA_NCCL(g_nccl.GetUniqueId(&id));
+  memcpy(id_out_128, &id, sizeof id);
+  return SA_OK;
+}
+
+int sa_comm_create_rank(sa_comm** out, int n_ranks, int rank, const void* id_128, int device) {
+  if (!out || !id_128) return fail(SA_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (n_ranks <= 0 || n_ranks > 64 || rank < 0 || rank >= n_ranks) return fail(SA_ERR_ARG, "bad rank %d of %d", rank, n_ranks);
+  int rc = load_nccl();
+  if (rc) return rc;
+  SA_ON_DEVICE(device);
+  ncclUniqueId id;
+  memcpy(&id, id_128, sizeof id);
+  ncclComm_t comm = nullptr;
+  SA_NCCL(g_nccl.CommInitRank(&comm, n_ranks, id, rank));
+  sa_comm* c = new sa_comm();
+  c->n_ranks = n_ranks;
+  c->rank = rank;
+  c->devices.push_back(device);
+  c->comms.push_back(comm);
+  c->gathered.push_back(nullptr);
+  c->gathered_elems.push_back(0);
+  *out = c;
+  return SA_OK;
+}
+
+int sa_comm_create(sa_comm** out, int n_gpus, const int* devices) {
+  if (!out) return fail(SA_ERR_ARG, "null out");
+  *out = nullptr;
+  if (n_gpus <= 0 || n_gpus > 64) return fail(SA_ERR_ARG, "n_gpus %d outside [1, 64]", n_gpus);
+  int rc = load_nccl();
+  if (rc) return rc;
+  sa_comm* c = new sa_comm();
+  c->n_ranks = n_gpus;
+  c->rank = -1;
+  for (int g = 0; g < n_gpus; ++g) c->devices.push_back(devices ? devices[g] : g);
+  c->comms.assign(n_gpus, nullptr);
+  c->gathered.assign(n_gpus, nullptr);
+  c->gathered_elems.assign(n_gpus, 0);
+  int prev = 0;
+  cudaGetDevice(&prev);
+  ncclResult_t r = g_nccl.CommInitAll(c->comms.data(), n_gpus, c->devices.data());
+  cudaSetDevice(prev);
+  if (r != ncclSuccess) {
+    delete c;
+    return fail(SA_ERR_COMM, "ncclCommInitAll failed: %s", g_nccl.GetErrorString(r));
+  }
+  *out = c;
+  return SA_OK;
+}
+
+void sa_comm_destroy(sa_comm* c) {
+  if (!c) return;
+  for (size_t i = 0; i < c->comms.size(); ++i) {
+    DeviceGuard g(c->devices[i]);
+    cudaDeviceSynchronize();
+    if (c->gathered[i]) cudaFree(c->gathered[i]);
+    if (c->comms[i] && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comms[i]);
+  }
+  delete c;
+}
+
+int sa_comm_ranks(const sa_comm* c) { return c ? c->n_ranks : -1; }
+
+namespace {
+int check_rank_comm(const sa_comm* c, const sa_engine* e) {
+  if (!c) return fail(SA_ERR_ARG, "null communicator");
+  if (c->rank < 0) return fail(SA_ERR_ARG, "single-process communicator: use sa_gather_merge");
+  if (c->devices[0] != e->device) return fail(SA_ERR_ARG, "communicator is on device %d, engine on %d", c->devices[0], e->device);
+  return SA_OK;
+}
+}  // namespace
+
+int sa_sharded_search(sa_comm* c, sa_engine* e, const void* q_bf16_dev, int nq, int k, int64_t row_offset,
+                      float* out_score_dev, int64_t* out_row_dev, uintptr_t stream) {
+  int rc = check_engine(e);
+  if (rc) return rc;
+  rc = check_rank_comm(c, e);
+  if (rc) return rc;
+  if (!out_score_dev || !out_row_dev) return fail(SA_ERR_ARG, "null buffer");
+  SA_ON_DEVICE(e->device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  SA_CUDA(cudaStreamWaitEvent(st, e->scratch_free, 0));
+  return sharded_search_on_stream(c, 0, e, static_cast<const uint16_t*>(q_bf16_dev), nq, k, row_offset, out_score_dev,
+                                  reinterpret_cast<long long*>(out_row_dev), st);
+}
+
+int sa_sharded_search_host_submit(sa_comm* c, sa_engine* e, int slot, const float* q_f32_host, int nq, int k,
+                                  int64_t row_offset) {
+  int rc = check_engine(e);
+  if (rc) return rc;
+  rc = check_rank_comm(c, e);
+  if (rc) return rc;
+  if (slot < 0 || slot >= kHostSlots) return fail(SA_ERR_ARG, "slot %d outside [0, %d)", slot, kHostSlots);
+  return host_submit(e, slot, q_f32_host, nq, k, c, 0, row_offset);
+}
+
+int sa_sharded_search_host_wait(sa_comm* c, sa_engine* e, int slot, float* out_score_host, int64_t* out_row_host) {
+  int rc = check_engine(e);
+  if (rc) return rc;
+  if (!c) return fail(SA_ERR_ARG, "null communicator");
+  if (slot < 0 || slot >= kHostSlots) return fail(SA_ERR_ARG, "slot %d outside [0, %d)", slot, kHostSlots);
+  return host_wait(e, slot, out_score_host, out_row_host, true);
+}
+
+int sa_gather_merge_submit(sa_comm* c, sa_engine* const* engines, int slot, const float* q_f32_host, int nq, int k,
+                           const int64_t* shard_offsets) {
+  if (!c || !engines || !shard_offsets) return fail(SA_ERR_ARG, "null argument");
+  if (c->rank >= 0) return fail(SA_ERR_ARG, "multi-process communicator: use sa_sharded_search*");
+  if (slot < 0 || slot >= kHostSlots) return fail(SA_ERR_ARG, "slot %d outside [0, %d)", slot, kHostSlots);
+  for (int g = 0; g < c->n_ranks; ++g) {
+    int rc = check_engine(engines[g]);
+    if (rc) return rc;
+    if (engines[g]->device != c->devices[g])
+      return fail(SA_ERR_ARG, "engine %d is on device %d, communicator rank %d on %d", g, engines[g]->device, g, c->devices[g]);
+  }
+  // every GPU gets the query block and runs the identical single-GPU path; the collectives of all local ranks are
+  // issued inside one NCCL group (a single thread drives all devices)
+  int rc = SA_OK;
+  for (int g = 0; g < c->n_ranks; ++g) {
+    rc = host_submit(engines[g], slot, q_f32_host, nq, k, c, g, shard_offsets[g], 1);
+    if (rc) return rc;
+  }
+  SA_NCCL(g_nccl.GroupStart());
+  for (int g = 0; g < c->n_ranks && rc == SA_OK; ++g)
+    rc = host_submit(engines[g], slot, q_f32_host, nq, k, c, g, shard_offsets[g], 2);
+  ncclResult_t r = g_nccl.GroupEnd();
+  if (rc) return rc;
+  if (r != ncclSuccess) return fail(SA_ERR_COMM, "ncclGroupEnd failed: %s", g_nccl.GetErrorString(r));
+  for (int g = 0; g < c->n_ranks; ++g) {
+    rc = host_submit(engines[g], slot, q_f32_host, nq, k, c, g, shard_offsets[g], 4);
+    if (rc) return rc;
+  }
+  return SA_OK;
+}
+
+int sa_gather_merge_wait(sa_comm* c, sa_engine* const* engines, int slot, float* out_score_host, int64_t* out_row_host) {
+  if (!c || !engines) return fail(SA_ERR_ARG, "null argument");
+  if (slot < 0 || slot >= kHostSlots) return fail(SA_ERR_ARG, "slot %d outside [0, %d)", slot, kHostSlots);
+  // every rank holds the same merged answer; hand out rank 0's and retire the other slots
+  int rc = host_wait(engines[0], slot, out_score_host, out_row_host, true);
+  for (int g = 1; g < c->n_ranks; ++g) {
+    sa_engine::HostSlot& sl = engines[g]->slot[slot];
+    if (sl.busy) {
+      DeviceGuard dg(engines[g]->device);
+      cudaEventSynchronize(sl.done);
+      sl.busy = false;
+    }
+  }
+  return rc;
+}
+
+int sa_gather_merge(sa_comm* c, sa_engine* const* engines, const float* q_f32_host, int nq, int k,
+                    const int64_t* shard_offsets, float* out_score_host, int64_t* out_row_host) {
+  int rc = sa_gather_merge_submit(c, engines, 0, q_f32_host, nq, k, shard_offsets);
+  if (rc) return rc;
+  return sa_gather_merge_wait(c, engines, 0, out_score_host, out_row_host);
 }
 
 namespace {
@@ -751,7 +1229,7 @@ int sa_last_timing(sa_engine* e, float* scan_ms, float* total_ms, double* bytes,
                    int* kernels) {
   if (!e) return fail(SA_ERR_ARG, "null engine");
   if (e->n_searches == 0) return fail(SA_ERR_ARG, "no search has run on this engine");
-  SA_CUDA(cudaSetDevice(e->device));
+  SA_ON_DEVICE(e->device);
   float scan = 0.f, tot = 0.f;
   const sa_engine::Timing* tm = nullptr;
   int rc = read_timing(e, 0, &scan, &tot, &tm);
@@ -768,7 +1246,7 @@ int sa_last_timing(sa_engine* e, float* scan_ms, float* total_ms, double* bytes,
 int sa_timing_mean(sa_engine* e, int n, float* scan_ms_mean, float* total_ms_mean, int* n_used) {
   if (!e || !scan_ms_mean || !total_ms_mean || !n_used) return fail(SA_ERR_ARG, "null argument");
   if (e->n_searches == 0) return fail(SA_ERR_ARG, "no search has run on this engine");
-  SA_CUDA(cudaSetDevice(e->device));
+  SA_ON_DEVICE(e->device);
   const int m = static_cast<int>(std::min<long long>(std::min(n, kTimingRing), e->n_searches));
   if (m <= 0) return fail(SA_ERR_ARG, "n must be positive");
   double ssum = 0, tsum = 0;
@@ -798,9 +1276,16 @@ int sa_set_option(sa_engine* e, const char* name, int64_t value) {
     e->opt_max_launch_qblocks = static_cast<int>(value);
     return SA_OK;
   }
-  if (!strcmp(name, "qpu2")) {
-    if (value < 0 || value > 2) return fail(SA_ERR_ARG, "qpu2 must be 0 (never), 1 (auto) or 2 (always)");
-    e->opt_qpu2 = static_cast<int>(value);
+  if (!strcmp(name, "force_fix")) {
+    e->opt_force_fix = value ? 1 : 0;
+    return SA_OK;
+  }
+  if (!strcmp(name, "count_fix")) {
+    e->opt_count_fix = value ? 1 : 0;
+    return SA_OK;
+  }
+  if (!strcmp(name, "profile")) {
+    e->opt_profile = value ? 1 : 0;
     return SA_OK;
   }
   if (!strcmp(name, "share_thresholds")) {
@@ -849,7 +1334,20 @@ int sa_get_info(const sa_engine* e, const char* name, int64_t* value) {
   else if (!strcmp(name, "max_k")) *value = e->max_k;
   else if (!strcmp(name, "last_grid")) *value = e->last_grid;
   else if (!strcmp(name, "dbg_times_ptr")) *value = static_cast<int64_t>(reinterpret_cast<uintptr_t>(e->dbg_times));
+  else if (!strcmp(name, "last_fix_entries")) *value = e->last_fix_entries;
+  else if (!strcmp(name, "eps_rel_e12")) *value = static_cast<int64_t>(static_cast<double>(scan_eps_rel(e->dim)) * 1e12);
   else return fail(SA_ERR_ARG, "unknown info '%s'", name);
+  return SA_OK;
+}
+
+int sa_scan_profile(sa_engine* e, int64_t* out_host, int max_ctas, int* n_ctas) {
+  if (!e || !out_host || !n_ctas) return fail(SA_ERR_ARG, "null argument");
+  static_assert(sizeof(sa::ScanProf) == 8 * sizeof(int64_t), "profile record is 8 x int64");
+  SA_ON_DEVICE(e->device);
+  const int n = std::min(std::min(max_ctas, e->last_grid), e->num_sms);
+  SA_CUDA(cudaDeviceSynchronize());
+  SA_CUDA(cudaMemcpy(out_host, e->prof, static_cast<size_t>(n) * sizeof(sa::ScanProf), cudaMemcpyDeviceToHost));
+  *n_ctas = n;
   return SA_OK;
 }
 
@@ -864,7 +1362,7 @@ int sa_debug_tile_dots(sa_engine* e, const void* q_bf16_dev, int nq, int tile, i
   const int rows_per_qb = 128 * cta_group;
   const int nqb = (nq + rows_per_qb - 1) / rows_per_qb;
   if (nq <= 0 || nqb * cta_group > e->num_sms) return fail(SA_ERR_CAPACITY, "nq too large for the debug hook");
-  SA_CUDA(cudaSetDevice(e->device));
+  SA_ON_DEVICE(e->device);
   CUtensorMap tq;
   rc = encode_rows_map(&tq, q_bf16_dev, static_cast<uint64_t>(nq), e->dim, sa::kBlockM);
   if (rc) return rc;
@@ -878,6 +1376,7 @@ int sa_debug_tile_dots(sa_engine* e, const void* q_bf16_dev, int nq, int tile, i
   sp.tl_count = 1;  // one tile lane: every unit walks all tiles, dumps `tile`
   sp.part_score = e->part_score;
   sp.part_idx = e->part_idx;
+  sp.part_drop = e->part_drop;
   sp.corpus_evict_first = 0;
   sp.lane_progress = nullptr;
   sp.max_drift = 0;
@@ -888,24 +1387,22 @@ int sa_debug_tile_dots(sa_engine* e, const void* q_bf16_dev, int nq, int tile, i
   sp.dbg_times = nullptr;
   sp.dbg_dots = out_dots_dev;
   sp.dbg_tile = tile;
-  return launch_scan_dispatch(cta_group, 16, 1, true, tq, e->tmap_c[cta_group - 1], sp, nqb * cta_group,
+  return launch_scan_dispatch(cta_group, 16, sa::kModeDots, tq, e->tmap_c[cta_group - 1], sp, nqb * cta_group,
                               reinterpret_cast<cudaStream_t>(stream));
 }
 
-int sa_debug_plan(int num_sms, int nq, int cta_group, int num_tiles, int max_launch_qblocks, int allow_qpu2, int* out,
-                  int max_out, int* n_launches) {
+int sa_debug_plan(int num_sms, int nq, int cta_group, int num_tiles, int max_launch_qblocks, int* out, int max_out,
+                  int* n_launches) {
   if (!out || !n_launches) return fail(SA_ERR_ARG, "null argument");
   if (num_sms < 2 || nq <= 0 || num_tiles < 0 || (cta_group != 1 && cta_group != 2))
     return fail(SA_ERR_ARG, "bad planning input");
-  std::vector<LaunchPlan> plan =
-      plan_search(num_sms, max_launch_qblocks, nq, cta_group, std::max(num_tiles, 1), allow_qpu2);
+  std::vector<LaunchPlan> plan = plan_search(num_sms, max_launch_qblocks, nq, cta_group, std::max(num_tiles, 1));
   if (static_cast<int>(plan.size()) > max_out) return fail(SA_ERR_CAPACITY, "plan has %zu launches", plan.size());
   for (size_t i = 0; i < plan.size(); ++i) {
-    out[5 * i + 0] = plan[i].q0;
-    out[5 * i + 1] = plan[i].nq;
-    out[5 * i + 2] = plan[i].nqb;
-    out[5 * i + 3] = plan[i].tl;
-    out[5 * i + 4] = plan[i].qpu;
+    out[4 * i + 0] = plan[i].q0;
+    out[4 * i + 1] = plan[i].nq;
+    out[4 * i + 2] = plan[i].nqb;
+    out[4 * i + 3] = plan[i].tl;
   }
   *n_launches = static_cast<int>(plan.size());
   return SA_OK;
@@ -941,10 +1438,10 @@ int sa_debug_merge_keys(const float* score, const int32_t* row, int n, uint64_t*
 }
 
 int sa_debug_list_insert(const float* score, const int32_t* row, int n, int list_len, const float* floor_after,
-                         float* out_score, int32_t* out_row) {
+                         float* out_score, int32_t* out_row, float* out_drop) {
   if (!score || !row || !out_score || !out_row || n < 0) return fail(SA_ERR_ARG, "bad argument");
-  if (list_len == 16) run_list<16>(score, row, n, floor_after, out_score, out_row);
-  else if (list_len == 32) run_list<32>(score, row, n, floor_after, out_score, out_row);
+  if (list_len == 16) run_list<16>(score, row, n, floor_after, out_score, out_row, out_drop);
+  else if (list_len == 32) run_list<32>(score, row, n, floor_after, out_score, out_row, out_drop);
   else return fail(SA_ERR_ARG, "list_len must be 16 or 32");
   return SA_OK;
 }

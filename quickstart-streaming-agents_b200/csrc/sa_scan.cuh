@@ -6,13 +6,18 @@
 //   tcgen05.mma  Q[128 x D] . C[256 x D]^T, fp32 accumulators in TMEM (two 256-column buffers)
 //   epilogue warps: tcgen05.ld -> scale by the row's 1/|c| -> per-thread (thread == query) sorted register list
 //
-// Nothing but the per-CTA candidate lists (kKL entries per query) leaves the SM.
+// Nothing but the per-CTA candidate lists (kKL entries per query, plus one "dropped" bound per query) leaves the SM.
 //
 // Work decomposition.  A "unit" is one CTA (kCG == 1, 128-query blocks) or one CTA pair (kCG == 2, 256-query
-// blocks, tcgen05 cta_group::2) and carries kQPU (1 or 2) query blocks.  Unit u owns slot = u % nslots (its query
-// blocks) and tile lane tl = u / nslots and walks corpus tiles tl, tl + TL, tl + 2 TL, ... (256 rows each), making
-// one pass per query block over each.  All units of one tile lane touch the same corpus tile at about the same
-// time (drift control below keeps it so): it crosses HBM once and is served from L2 to the others.
+// blocks, tcgen05 cta_group::2).  Unit u owns query block qb = u % nqb and tile lane tl = u / nqb and walks corpus
+// tiles tl, tl + TL, tl + 2 TL, ... (256 rows each).  All units of one tile lane touch the same corpus tile at about
+// the same time (drift control below keeps it so): it crosses HBM once and is served from L2 to the others.
+//
+// Exactness contract with the merge kernel (sa_aux.cuh).  A thread's list holds the kKL best rows of its tile lane by
+// the scan's approximate score a = fp32_accumulate(q.c) * (1/|c|), and `drop` is an upper bound on the approximate
+// score of every row of the lane that is NOT in the list (evicted, rejected by the own threshold, or rejected by the
+// bound shared between lanes).  The merge kernel turns (lists, drops) into either a certificate that the exactly
+// re-scored candidates contain the true top-k, or a work item for the exact fallback scan.
 #pragma once
 #include "sm100_ptx.cuh"
 #include <cmath>
@@ -26,6 +31,12 @@ constexpr int kBlockK = 64;   // bf16 per K slice = 128 B = one swizzle atom
 constexpr int kUmmaK = 16;
 constexpr int kScanThreads = 256;  // w0 TMA, w1 MMA, w2 TMEM alloc, w3 idle, w4..7 epilogue
 constexpr int kTmemCols = 512;
+constexpr int kChunk = 32;         // TMEM columns per tcgen05.ld
+
+// kMode of the scan kernel
+constexpr int kModeProd = 0;   // production
+constexpr int kModeDots = 1;   // test hook: also dump the raw accumulators of one tile
+constexpr int kModeProf = 2;   // profiling: per-role wait / busy cycle counters (ScanParams::prof)
 
 template <int kCG>
 struct ScanCfg {
@@ -34,33 +45,47 @@ struct ScanCfg {
   static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
   static constexpr uint32_t kBBytes = kBRows * kBlockK * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  static constexpr uint32_t kIcBytes = 2 * kBlockN * sizeof(float);
+  static constexpr uint32_t kIcBytes = 4 * kBlockN * sizeof(float);  // one 256-float scale vector per epilogue warp
   static constexpr uint32_t kBarBytes = (2 * kStages + 4) * 8 + 16;
   // +1024: the dynamic smem base is aligned up to 1024 B by hand (SWIZZLE_128B requirement).
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kIcBytes + kBarBytes + 1024;
 };
 
+// Per-CTA profile record (kModeProf): SM cycles, summed over the kernel.
+struct ScanProf {
+  long long prod_wait_empty;   // TMA producer blocked on a free smem slot
+  long long mma_wait_full;     // MMA issuer blocked on TMA data
+  long long mma_wait_tempty;   // MMA issuer blocked on the epilogue (accumulator not drained)
+  long long epi_wait_tfull;    // epilogue warp 0 blocked on the MMA (accumulator not complete)
+  long long epi_busy;          // epilogue warp 0 working on an accumulator
+  long long epi_slow_chunks;   // 32-column chunks of epilogue warp 0 that took the insertion path
+  long long total;             // CTA lifetime
+  long long tiles;             // tiles walked
+};
+
 struct ScanParams {
-  const float* inv_norm;  // [capacity] 1/|row| over the bf16-rounded row, 0 for an all-zero row
+  const float* inv_norm;  // [capacity] 1/|row| over the bf16-rounded row, 0 for an all-zero row; 16-byte aligned
   long long n_rows;       // committed rows (epoch snapshot); rows >= n_rows are masked
   int nq;                 // queries covered by tmap_q
   int num_kb;             // D / 64
   int num_tiles;          // ceil(n_rows / 256)
   int nqb;                // query blocks of 128*kCG rows
   int tl_count;           // tile lanes (TL)
-  float* part_score;      // [gridDim.x][128][kQPU][kKL]
-  int* part_idx;          // [gridDim.x][128][kQPU][kKL]
+  float* part_score;      // [gridDim.x][128][kKL]
+  int* part_idx;          // [gridDim.x][128][kKL]
+  float* part_drop;       // [gridDim.x][128]  upper bound on the approximate score of the lane's rows not in the list
   int corpus_evict_first; // 1: corpus tiles are read by a single query block -> stream them through L2
-  int* lane_progress;     // [tl_count][nslots] tiles whose loads each unit has issued (zeroed before launch), or nullptr
-  int unit_map;           // 0: unit = tl*nslots + slot (lane-mates adjacent), 1: unit = slot*TL + tl (lane-mates TL apart)
+  int* lane_progress;     // [tl_count][nqb] tiles whose loads each unit has issued (zero at launch), or nullptr
+  int unit_map;           // 0: unit = tl*nqb + qb (lane-mates adjacent), 1: unit = qb*TL + tl (lane-mates TL apart)
   int max_drift;          // lead (in tiles) over the slowest lane-mate that is not paced
   int pace_gain;          // SM cycles of delay per K-slice issue per tile of lead beyond max_drift (0 = free-running)
   int pace_max;           // cap of that delay
   unsigned* thr_shared;   // [nqb*128*kCG] per-query lower bound on the kKL-th best score, order-preserving keys
-                          // (zeroed before launch), or nullptr: lanes then learn their thresholds alone
+                          // (zero at launch), or nullptr: lanes then learn their thresholds alone
   long long* dbg_times;   // optional [gridDim.x][2]: globaltimer at CTA start / end (ns), for drift studies
-  float* dbg_dots;        // debug builds only: raw accumulators of (unit 0 .. nqb-1, tile dbg_tile) [nqb*128*kCG][256]
+  float* dbg_dots;        // kModeDots only: raw accumulators of (unit 0 .. nqb-1, tile dbg_tile) [nqb*128*kCG][256]
   int dbg_tile;
+  ScanProf* prof;         // kModeProf only: [gridDim.x]
 };
 
 // Bit casts usable on both sides of the compiler: the device path is the intrinsic, the host path (used only by the
@@ -100,6 +125,18 @@ __host__ __device__ __forceinline__ float float_below(float x) {
   return bits_f32(0x80000001u);  // below +-0: the smallest negative denormal
 }
 
+// max that ignores a NaN operand (device: FMNMX; host: the same rule spelled out for the CPU unit tests)
+__host__ __device__ __forceinline__ float max_nn(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return fmaxf(a, b);
+#else
+  if (a != a) return b;
+  if (b != b) return a;
+  if (a == b) return (f32_bits(a) & 0x80000000u) ? b : a;  // max(+0, -0) = +0, as FMNMX
+  return a > b ? a : b;
+#endif
+}
+
 // Sorted (descending score, ascending row on ties) insertion into a register-resident list.
 // Precondition: s > sc[kKL-1].  Rows reach a thread in ascending order, so a strict compare keeps the
 // lower row index ahead of an equal score.
@@ -130,84 +167,149 @@ struct TopList {
   float thr;        // current insertion threshold = max(own kKL-th best, thr_floor)
   float thr_floor;  // largest float strictly below the bound shared by the other tile lanes
   float published;  // last own kKL-th best written to the shared bound
+  float drop;       // max approximate score of any row this thread saw and does not hold (NaN-free; -inf = none)
+  unsigned nxt_key; // shared bound fetched at the end of the previous accumulator (0 = nothing published yet)
   unsigned* slot;   // this query's shared bound (or nullptr)
-  __device__ __forceinline__ void init(unsigned* shared_slot) {
+  __host__ __device__ __forceinline__ void init(unsigned* shared_slot) {
+#ifdef __CUDA_ARCH__
 #pragma unroll
+#endif
     for (int i = 0; i < kKL; ++i) {
       sc[i] = -INFINITY;
       id[i] = -1;
     }
-    thr = thr_floor = published = -INFINITY;
+    thr = thr_floor = published = drop = -INFINITY;
+    nxt_key = 0u;
     slot = shared_slot;
+  }
+  // a bound published by another tile lane becomes visible
+  __host__ __device__ __forceinline__ void apply_shared(unsigned key) {
+    if (key != 0u) {
+      thr_floor = float_below(key_to_float(key));
+      thr = max_nn(thr, thr_floor);
+    }
   }
 };
 
-// Epilogue of one accumulator: 256 columns of this thread's TMEM lane -> scaled scores -> list.
-template <int kKL, bool kDebug>
-__device__ __forceinline__ void epilogue_accumulator(TopList<kKL>& L, uint32_t taddr, const float4* ic4, int row0,
-                                                     float* dbg_row) {
-  if (L.slot != nullptr) {  // refresh the shared bound once per accumulator
-    const unsigned key = ld_relaxed_gpu_u32(L.slot);
-    if (key != 0u) {
-      L.thr_floor = float_below(key_to_float(key));
-      L.thr = fmaxf(L.thr, L.thr_floor);
-    }
+// The per-value rule of the epilogue for one group of four consecutive rows whose maximum `m` already exceeds the
+// threshold: insert in (score desc, row asc) order while anything qualifies; account what does not in `drop`.
+template <int kKL>
+__host__ __device__ __forceinline__ void group_insert(TopList<kKL>& L, float s0, float s1, float s2, float s3, float m,
+                                                      int row) {
+  while (m > L.thr) {  // rare after warm-up: ~kKL/n per value
+    const int j = (s0 == m) ? 0 : (s1 == m) ? 1 : (s2 == m) ? 2 : 3;  // lowest row among equals first
+    const float sj = (j == 0) ? s0 : (j == 1) ? s1 : (j == 2) ? s2 : s3;  // == m, but keeps the element's own sign of zero
+    L.drop = max_nn(L.drop, L.sc[kKL - 1]);                           // the evicted tail (-inf while the list fills)
+    list_insert<kKL>(L.sc, L.id, sj, row + j);
+    L.thr = max_nn(L.sc[kKL - 1], L.thr_floor);
+    s0 = (j == 0) ? -INFINITY : s0;
+    s1 = (j == 1) ? -INFINITY : s1;
+    s2 = (j == 2) ? -INFINITY : s2;
+    s3 = (j == 3) ? -INFINITY : s3;
+    m = max_nn(max_nn(s0, s1), max_nn(s2, s3));
   }
-#pragma unroll 1
-  for (int c = 0; c < kBlockN / 32; ++c) {
-    float v[32];
-    __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent insert path
-    tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
-    tmem_ld_wait(v);
-    if constexpr (kDebug) {
-      if (dbg_row != nullptr) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) dbg_row[c * 32 + j] = v[j];
-      }
-    }
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      const float4 w = ic4[c * 8 + g];
-      float s0 = v[4 * g + 0] * w.x;
-      float s1 = v[4 * g + 1] * w.y;
-      float s2 = v[4 * g + 2] * w.z;
-      float s3 = v[4 * g + 3] * w.w;
-      float m = fmaxf(fmaxf(s0, s1), fmaxf(s2, s3));
-      while (m > L.thr) {  // rare after warm-up: ~kKL/n per value
-        const int j = (s0 == m) ? 0 : (s1 == m) ? 1 : (s2 == m) ? 2 : 3;  // lowest row among equals first
-        list_insert<kKL>(L.sc, L.id, m, row0 + c * 32 + g * 4 + j);
-        L.thr = fmaxf(L.sc[kKL - 1], L.thr_floor);
-        s0 = (j == 0) ? -INFINITY : s0;
-        s1 = (j == 1) ? -INFINITY : s1;
-        s2 = (j == 2) ? -INFINITY : s2;
-        s3 = (j == 3) ? -INFINITY : s3;
-        m = fmaxf(fmaxf(s0, s1), fmaxf(s2, s3));
-      }
-    }
-  }
-  if (L.slot != nullptr && L.sc[kKL - 1] > L.published) {  // list full and its tail improved: tell the other lanes
-    L.published = L.sc[kKL - 1];
-    atomicMax(L.slot, float_to_key(L.published));
-  }
+  L.drop = max_nn(L.drop, m);  // whatever is left of the group was rejected (NaN = masked rows: ignored)
 }
 
-// kQPU = query blocks per unit.  With kQPU == 2 a unit makes two passes over every corpus tile, one per query block
-// (the second pass re-reads the tile from L2, where the first pass just put it) and keeps two candidate lists.  It
-// exists to fill the machine: 4 query blocks on 74 SM pairs are 4 x 18 lanes = 72 pairs with kQPU == 1, but
-// 2 x 37 lanes = 74 pairs with kQPU == 2, and a tile is shared by 2 units instead of 4.
-template <int kCG, int kKL, int kQPU, bool kDebug>
+// One 32-column chunk: scale, reduce to the chunk maximum with full instruction-level parallelism, and only when that
+// beats the threshold (probability ~ 32 kKL / n after n rows) walk the groups.  Returns true if the slow path ran.
+template <int kKL>
+__host__ __device__ __forceinline__ bool chunk_process(TopList<kKL>& L, float (&v)[kChunk], const float (&w)[kChunk],
+                                                       int row_base) {
+  float g[8];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int i = 0; i < 8; ++i) {
+    v[4 * i + 0] *= w[4 * i + 0];
+    v[4 * i + 1] *= w[4 * i + 1];
+    v[4 * i + 2] *= w[4 * i + 2];
+    v[4 * i + 3] *= w[4 * i + 3];
+    g[i] = max_nn(max_nn(v[4 * i + 0], v[4 * i + 1]), max_nn(v[4 * i + 2], v[4 * i + 3]));
+  }
+  const float m = max_nn(max_nn(max_nn(g[0], g[1]), max_nn(g[2], g[3])), max_nn(max_nn(g[4], g[5]), max_nn(g[6], g[7])));
+  if (!(m > L.thr)) {
+    L.drop = max_nn(L.drop, m);
+    return false;
+  }
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int i = 0; i < 8; ++i)
+    group_insert<kKL>(L, v[4 * i + 0], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3], g[i], row_base + 4 * i);
+  return true;
+}
+
+#ifdef __CUDACC__
+// Epilogue of one accumulator: 256 columns of this thread's TMEM lane -> scaled scores -> list.
+// `ic` is this warp's private 256-float scale vector in shared memory (broadcast reads).
+template <int kKL, int kMode>
+__device__ __forceinline__ int epilogue_accumulator(TopList<kKL>& L, uint32_t taddr, const float* ic, int row0,
+                                                    float* dbg_row) {
+  L.apply_shared(L.nxt_key);
+  int slow = 0;
+  float va[kChunk], vb[kChunk], w[kChunk];
+  const float4* ic4 = reinterpret_cast<const float4*>(ic);
+  auto load_w = [&](int c) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 x = ic4[c * 8 + i];
+      w[4 * i + 0] = x.x;
+      w[4 * i + 1] = x.y;
+      w[4 * i + 2] = x.z;
+      w[4 * i + 3] = x.w;
+    }
+  };
+  auto dump = [&](int c, const float (&v)[kChunk]) {
+    if constexpr (kMode == kModeDots) {
+      if (dbg_row != nullptr) {
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j) dbg_row[c * kChunk + j] = v[j];
+      }
+    }
+  };
+  __syncwarp();  // tcgen05.ld / wait::ld are .sync.aligned
+  tmem_ld_32x32(taddr, va);
+#pragma unroll 1
+  for (int c = 0; c < kBlockN / kChunk; c += 2) {
+    // chunk c is in flight into va: fetch its scales, wait, start chunk c+1 into vb, then work on va
+    load_w(c);
+    tmem_ld_wait(va);
+    tmem_ld_32x32(taddr + static_cast<uint32_t>((c + 1) * kChunk), vb);
+    dump(c, va);
+    slow += chunk_process<kKL>(L, va, w, row0 + c * kChunk) ? 1 : 0;
+    __syncwarp();  // reconverge after the divergent insertion path
+    load_w(c + 1);
+    tmem_ld_wait(vb);
+    if (c + 2 < kBlockN / kChunk) tmem_ld_32x32(taddr + static_cast<uint32_t>((c + 2) * kChunk), va);
+    dump(c + 1, vb);
+    slow += chunk_process<kKL>(L, vb, w, row0 + (c + 1) * kChunk) ? 1 : 0;
+    __syncwarp();
+  }
+  if (L.slot != nullptr) {
+    if (L.sc[kKL - 1] > L.published) {  // list full and its tail improved: tell the other lanes
+      L.published = L.sc[kKL - 1];
+      atomicMax(L.slot, float_to_key(L.published));
+    }
+    L.nxt_key = ld_relaxed_gpu_u32(L.slot);  // consumed at the start of the next accumulator: latency hidden
+  }
+  return slow;
+}
+
+template <int kCG, int kKL, int kMode>
 __global__ void __launch_bounds__(kScanThreads, 1)
 sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                const ScanParams p) {
   using Cfg = ScanCfg<kCG>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kRowsPerQb = kBlockM * kCG;
+  constexpr bool kProf = (kMode == kModeProf);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
-  float* icbuf = reinterpret_cast<float*>(smem_gen + kStages * Cfg::kStageBytes);  // [2][256]
+  float* icbuf = reinterpret_cast<float*>(smem_gen + kStages * Cfg::kStageBytes);  // [4 warps][256]
   const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes + Cfg::kIcBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
@@ -223,13 +325,13 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   const uint32_t rank = (kCG == 2) ? cluster_ctarank() : 0u;
   const int unit = blockIdx.x / kCG;
   const int TL = p.tl_count;
-  const int nslots = (p.nqb + kQPU - 1) / kQPU;  // units per tile lane
-  const int slot = p.unit_map == 0 ? unit % nslots : unit / TL;
-  const int tl = p.unit_map == 0 ? unit / nslots : unit % TL;
-  const int qb0 = slot * kQPU;                    // first query block of this unit
-  const int npass = min(kQPU, p.nqb - qb0);       // passes over each tile (the last slot of an odd nqb has one)
+  const int nqb = p.nqb;  // units per tile lane
+  const int qb = p.unit_map == 0 ? unit % nqb : unit / TL;
+  const int tl = p.unit_map == 0 ? unit / nqb : unit % TL;
 
   // ------------------------------------------------------------------ one-time setup
+  long long t_start = 0;
+  if constexpr (kProf) t_start = clock64();
   if (p.dbg_times != nullptr && threadIdx.x == 0) p.dbg_times[2 * blockIdx.x] = globaltimer_ns();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -263,6 +365,7 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       const uint64_t c_hint = p.corpus_evict_first ? kEvictFirst : kEvictNormal;
       int stage = 0;
       uint32_t phase = 0;
+      long long waited = 0;
       // Drift control between the units of a tile lane.  Units that share a corpus tile run identical work but at
       // slightly different speeds (measured: ~3 % spread), so over thousands of tiles they drift tens of tiles
       // apart; once the spread exceeds what L2 holds, every unit re-reads its tiles from HBM (measured 3.05x the
@@ -272,42 +375,50 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       // delays every K-slice issue by pace_gain cycles per extra tile of lead (capped).  The kernel's duration is
       // set by its slowest unit anyway, so slowing the fast ones is free; it is only a hint (no waiting on
       // anyone), hence no co-residency assumption and no deadlock.
-      const bool lockstep = p.lane_progress != nullptr && p.pace_gain > 0 && nslots > 1 && rank == 0;
+      const bool lockstep = p.lane_progress != nullptr && p.pace_gain > 0 && nqb > 1 && rank == 0;
       int pace = 0;
       int tile_no = 0;
+      const int q_row = qb * kRowsPerQb + static_cast<int>(rank) * kBlockM;
       for (int t = tl; t < p.num_tiles; t += TL, ++tile_no) {
         if (lockstep) {
-          const int* pr = p.lane_progress + tl * nslots;
+          const int* pr = p.lane_progress + tl * nqb;
           int slowest = tile_no;
-          for (int j = 0; j < nslots; ++j) slowest = min(slowest, ld_relaxed_gpu(pr + j));
+          for (int j = 0; j < nqb; ++j) slowest = min(slowest, ld_relaxed_gpu(pr + j));
           pace = min(max(tile_no - slowest - p.max_drift, 0) * p.pace_gain, p.pace_max);
         }
-        for (int s = 0; s < npass; ++s) {
-          const int q_row = (qb0 + s) * kRowsPerQb + static_cast<int>(rank) * kBlockM;
-          for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          if constexpr (kProf) {
+            const long long c0 = clock64();
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            if (pace > 0) {
-              const long long c0 = clock64();
-              while (clock64() - c0 < pace) {
-              }
-            }
-            if constexpr (kCG == 1) {
-              mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-              tma_load_2d(a_smem(stage), &tmap_q, full_bar(stage), kb * kBlockK, q_row, kEvictLast);
-              tma_load_2d(b_smem(stage), &tmap_c, full_bar(stage), kb * kBlockK, t * kBlockN, c_hint);
-            } else {
-              if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
-              tma_load_2d_pair(a_smem(stage), &tmap_q, full_bar(stage), kb * kBlockK, q_row, kEvictLast);
-              tma_load_2d_pair(b_smem(stage), &tmap_c, full_bar(stage), kb * kBlockK,
-                               t * kBlockN + static_cast<int>(rank) * Cfg::kBRows, c_hint);
-            }
-            if (++stage == kStages) {
-              stage = 0;
-              phase ^= 1u;
+            waited += clock64() - c0;
+          } else {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+          }
+          if (pace > 0) {
+            const long long c0 = clock64();
+            while (clock64() - c0 < pace) {
             }
           }
+          if constexpr (kCG == 1) {
+            mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+            tma_load_2d(a_smem(stage), &tmap_q, full_bar(stage), kb * kBlockK, q_row, kEvictLast);
+            tma_load_2d(b_smem(stage), &tmap_c, full_bar(stage), kb * kBlockK, t * kBlockN, c_hint);
+          } else {
+            if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+            tma_load_2d_pair(a_smem(stage), &tmap_q, full_bar(stage), kb * kBlockK, q_row, kEvictLast);
+            tma_load_2d_pair(b_smem(stage), &tmap_c, full_bar(stage), kb * kBlockK,
+                             t * kBlockN + static_cast<int>(rank) * Cfg::kBRows, c_hint);
+          }
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
-        if (lockstep) st_relaxed_gpu(p.lane_progress + tl * nslots + slot, tile_no + 1);
+        if (lockstep) st_relaxed_gpu(p.lane_progress + tl * nqb + qb, tile_no + 1);
+      }
+      if constexpr (kProf) {
+        p.prof[blockIdx.x].prod_wait_empty = waited;
+        p.prof[blockIdx.x].tiles = tile_no;
       }
     }
   } else if (warp == 1) {
@@ -317,103 +428,126 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = tl; t < p.num_tiles; t += TL) {
-        for (int s = 0; s < npass; ++s, ++it) {
-          const int a = it & 1;
-          const uint32_t aph = (it >> 1) & 1u;
+      long long w_full = 0, w_tempty = 0;
+      for (int t = tl; t < p.num_tiles; t += TL, ++it) {
+        const int a = it & 1;
+        const uint32_t aph = (it >> 1) & 1u;
+        if constexpr (kProf) {
+          const long long c0 = clock64();
+          mbar_wait(tempty_bar(a), aph ^ 1u);
+          w_tempty += clock64() - c0;
+        } else {
           mbar_wait(tempty_bar(a), aph ^ 1u);  // epilogue has drained this accumulator
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(a * kBlockN);
-          for (int kb = 0; kb < p.num_kb; ++kb) {
-            mbar_wait(full_bar(stage), phase);
-            tc_fence_after();
-            const uint64_t a_desc = make_kmajor_sw128_desc(a_smem(stage));
-            const uint64_t b_desc = make_kmajor_sw128_desc(b_smem(stage));
-#pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-              // +32 B along K inside the 128-B swizzle atom = +2 in the (addr >> 4) field
-              umma_bf16<kCG>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            }
-            umma_commit<kCG>(empty_bar(stage));  // frees the smem slot (in both CTAs) once these MMAs retire
-            if (++stage == kStages) {
-              stage = 0;
-              phase ^= 1u;
-            }
-          }
-          umma_commit<kCG>(tfull_bar(a));  // accumulator complete -> epilogue
         }
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(a * kBlockN);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          if constexpr (kProf) {
+            const long long c0 = clock64();
+            mbar_wait(full_bar(stage), phase);
+            w_full += clock64() - c0;
+          } else {
+            mbar_wait(full_bar(stage), phase);
+          }
+          tc_fence_after();
+          const uint64_t a_desc = make_kmajor_sw128_desc(a_smem(stage));
+          const uint64_t b_desc = make_kmajor_sw128_desc(b_smem(stage));
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // +32 B along K inside the 128-B swizzle atom = +2 in the (addr >> 4) field
+            umma_bf16<kCG>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit<kCG>(empty_bar(stage));  // frees the smem slot (in both CTAs) once these MMAs retire
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit<kCG>(tfull_bar(a));  // accumulator complete -> epilogue
+      }
+      if constexpr (kProf) {
+        p.prof[blockIdx.x].mma_wait_full = w_full;
+        p.prof[blockIdx.x].mma_wait_tempty = w_tempty;
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: thread == query row; 4 warps cover the 128 TMEM lanes =====
+    // ===== epilogue: thread == query row; 4 warps cover the 128 TMEM lanes; the warps never synchronise with each
+    // other (each stages its own copy of the tile's 256 scales), only with the MMA issuer through the mbarriers =====
     const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
     const int et = ew * 32 + lane;
+    float* ic = icbuf + ew * kBlockN;
     // Threshold sharing.  A thread's list only ever sees its own tile lane, so alone it needs ~kKL*ln(n) insertions
     // to warm up, and a warp pays for every lane's insertions.  But if ANY lane already holds kKL rows scoring >= x
     // for this query, no row scoring < x can be in the query's global top-kKL.  So each epilogue thread publishes its
     // kKL-th best (atomicMax on an order-preserving key) and reads the shared bound once per accumulator: every lane
     // gets the threshold of the whole machine's progress, and the warm-up tail disappears.  The shared bound admits
     // ties (>=), the thread's own bound stays strict (>), so tie-breaking by row is unchanged.
-    auto query_of = [&](int s) { return (qb0 + s) * kRowsPerQb + static_cast<int>(rank) * kBlockM + et; };
-    auto shared_slot = [&](int s) -> unsigned* {
-      return (p.thr_shared != nullptr && s < npass && query_of(s) < p.nq) ? p.thr_shared + query_of(s) : nullptr;
-    };
-    TopList<kKL> L0, L1;
-    L0.init(shared_slot(0));
-    L1.init(kQPU > 1 ? shared_slot(1) : nullptr);
+    const int query = qb * kRowsPerQb + static_cast<int>(rank) * kBlockM + et;
+    TopList<kKL> L;
+    L.init((p.thr_shared != nullptr && query < p.nq) ? p.thr_shared + query : nullptr);
 
-    auto load_ic = [&](int t, float& x0, float& x1) {
-      const long long r0 = static_cast<long long>(t) * kBlockN + 2 * et;
-      x0 = (r0 < p.n_rows) ? __ldg(p.inv_norm + r0) : 0.f;
-      x1 = (r0 + 1 < p.n_rows) ? __ldg(p.inv_norm + r0 + 1) : 0.f;
+    // Scales of tile t: lane l fetches rows [8l, 8l+8) (two 16-byte loads), masks rows past the committed prefix
+    // and all-zero rows with NaN (NaN never compares greater than a threshold, so they cannot enter a list and
+    // are ignored by every max), and the warp shares them through its private smem vector.
+    float4 nx0 = make_float4(0.f, 0.f, 0.f, 0.f), nx1 = nx0;
+    auto fetch_ic = [&](int t) {
+      const long long r0 = static_cast<long long>(t) * kBlockN + 8 * lane;
+      const float4* src = reinterpret_cast<const float4*>(p.inv_norm + r0);
+      if (r0 + 8 <= p.n_rows) {
+        nx0 = __ldg(src);
+        nx1 = __ldg(src + 1);
+      } else {
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = (r0 + j < p.n_rows) ? __ldg(p.inv_norm + r0 + j) : 0.f;
+        nx0 = make_float4(x[0], x[1], x[2], x[3]);
+        nx1 = make_float4(x[4], x[5], x[6], x[7]);
+      }
     };
-    float nxt0 = 0.f, nxt1 = 0.f;
-    if (tl < p.num_tiles) load_ic(tl, nxt0, nxt1);
+    if (tl < p.num_tiles) fetch_ic(tl);
 
+    long long w_tfull = 0, busy = 0, slow_chunks = 0;
     int it = 0;
-    for (int t = tl; t < p.num_tiles; t += TL) {
-      // Rows past the committed prefix and all-zero rows get a NaN scale: NaN never compares greater than the
-      // threshold, so they can not enter a list.
+    for (int t = tl; t < p.num_tiles; t += TL, ++it) {
       const float qnan = __int_as_float(0x7fc00000);
-      const float2 scale = make_float2(nxt0 > 0.f ? nxt0 : qnan, nxt1 > 0.f ? nxt1 : qnan);
-      if (t + TL < p.num_tiles) load_ic(t + TL, nxt0, nxt1);  // prefetch the next tile's inverse norms
-      const int row0 = t * kBlockN;
-      for (int s = 0; s < npass; ++s, ++it) {
-        const int a = it & 1;
-        const uint32_t aph = (it >> 1) & 1u;
-        float* ic = icbuf + a * kBlockN;
-        reinterpret_cast<float2*>(ic)[et] = scale;
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue-only named barrier: ic[] visible
-
-        mbar_wait(tfull_bar(a), aph);
-        tc_fence_after();
-        const uint32_t taddr =
-            tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(a * kBlockN);
-        const float4* ic4 = reinterpret_cast<const float4*>(ic);
-        float* dbg_row = nullptr;
-        if constexpr (kDebug) {
-          if (p.dbg_dots != nullptr && t == p.dbg_tile)
-            dbg_row = p.dbg_dots + static_cast<size_t>(query_of(s)) * kBlockN;
-        }
-        if (kQPU == 1 || s == 0)
-          epilogue_accumulator<kKL, kDebug>(L0, taddr, ic4, row0, dbg_row);
+      auto sc = [&](float x) { return x > 0.f ? x : qnan; };
+      float4* dst = reinterpret_cast<float4*>(ic + 8 * lane);
+      dst[0] = make_float4(sc(nx0.x), sc(nx0.y), sc(nx0.z), sc(nx0.w));
+      dst[1] = make_float4(sc(nx1.x), sc(nx1.y), sc(nx1.z), sc(nx1.w));
+      if (t + TL < p.num_tiles) fetch_ic(t + TL);  // prefetch the next tile's inverse norms
+      __syncwarp();                                // ic[] visible to the whole warp
+      const int a = it & 1;
+      const uint32_t aph = (it >> 1) & 1u;
+      long long c0 = 0;
+      if constexpr (kProf) c0 = clock64();
+      mbar_wait(tfull_bar(a), aph);
+      tc_fence_after();
+      long long c1 = 0;
+      if constexpr (kProf) c1 = clock64();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(a * kBlockN);
+      float* dbg_row = nullptr;
+      if constexpr (kMode == kModeDots) {
+        if (p.dbg_dots != nullptr && t == p.dbg_tile) dbg_row = p.dbg_dots + static_cast<size_t>(query) * kBlockN;
+      }
+      const int slow = epilogue_accumulator<kKL, kMode>(L, taddr, ic, t * kBlockN, dbg_row);
+      tc_fence_before();
+      __syncwarp();  // also orders this tile's ic[] reads before the next tile's writes
+      if (lane == 0) {
+        if constexpr (kCG == 1)
+          mbar_arrive(tempty_bar(a));
         else
-          epilogue_accumulator<kKL, kDebug>(L1, taddr, ic4, row0, dbg_row);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if constexpr (kCG == 1)
-            mbar_arrive(tempty_bar(a));
-          else
-            mbar_arrive_cluster(tempty_bar(a), 0);  // the MMA issuer lives in the pair's leader CTA
-        }
+          mbar_arrive_cluster(tempty_bar(a), 0);  // the MMA issuer lives in the pair's leader CTA
+      }
+      if constexpr (kProf) {
+        w_tfull += c1 - c0;
+        busy += clock64() - c1;
+        slow_chunks += slow;
       }
     }
 
-    // The only global write of the scan: this CTA's candidate list(s) for each of its queries.
-    auto write_list = [&](const TopList<kKL>& L, int s) {
-      if (s >= npass || query_of(s) >= p.nq) return;
-      const size_t o = ((static_cast<size_t>(blockIdx.x) * kBlockM + et) * kQPU + s) * kKL;
+    // The only global writes of the scan: this CTA's candidate list and drop bound for each of its queries.
+    if (query < p.nq) {
+      const size_t o = (static_cast<size_t>(blockIdx.x) * kBlockM + et) * kKL;
       float4* ps = reinterpret_cast<float4*>(p.part_score + o);
       int4* pi = reinterpret_cast<int4*>(p.part_idx + o);
 #pragma unroll
@@ -421,20 +555,30 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         ps[i] = make_float4(L.sc[4 * i], L.sc[4 * i + 1], L.sc[4 * i + 2], L.sc[4 * i + 3]);
         pi[i] = make_int4(L.id[4 * i], L.id[4 * i + 1], L.id[4 * i + 2], L.id[4 * i + 3]);
       }
-    };
-    write_list(L0, 0);
-    if constexpr (kQPU > 1) write_list(L1, 1);
+      p.part_drop[static_cast<size_t>(blockIdx.x) * kBlockM + et] = L.drop;
+    }
+    if constexpr (kProf) {
+      if (ew == 0 && lane == 0) {
+        p.prof[blockIdx.x].epi_wait_tfull = w_tfull;
+        p.prof[blockIdx.x].epi_busy = busy;
+        p.prof[blockIdx.x].epi_slow_chunks = slow_chunks;
+      }
+    }
   }
 
   // ------------------------------------------------------------------ teardown
   tc_fence_before();
   __syncthreads();
   if (p.dbg_times != nullptr && threadIdx.x == 0) p.dbg_times[2 * blockIdx.x + 1] = globaltimer_ns();
+  if constexpr (kProf) {
+    if (threadIdx.x == 0) p.prof[blockIdx.x].total = clock64() - t_start;
+  }
   if constexpr (kCG == 2) cluster_sync_all();  // the peer may still be signalling our barriers / reading our smem
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<kCG>(tmem_base, kTmemCols);
   }
 }
+#endif  // __CUDACC__
 
 }  // namespace sa

@@ -30,6 +30,21 @@ def _ptr(t: torch.Tensor | None) -> int:
     return 0 if t is None else t.data_ptr()
 
 
+HIT_DTYPE = np.dtype([("score", "<f8"), ("row", "<i8")])   # sa_hit of include/sa_api.h
+
+
+def pinned_array(shape, dtype=np.float32) -> np.ndarray:
+    """A page-locked numpy array (sa_host_alloc), freed (sa_host_free) when its last view is garbage-collected."""
+    import weakref
+    lib = capi.load()
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    capi.check(lib.sa_host_alloc(C.byref(p), max(nbytes, 1)), "sa_host_alloc")
+    buf = (C.c_char * nbytes).from_address(p.value)
+    weakref.finalize(buf, lib.sa_host_free, C.c_void_p(p.value))
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
 class VectorIndex:
     """A row shard of the corpus resident in HBM: bf16 rows [capacity, dim] + fp32 inverse norms [capacity]."""
 
@@ -48,19 +63,17 @@ class VectorIndex:
         capi.check(self.lib.sa_engine_create(C.byref(h), self.device, self.dim, self.capacity, self.max_batch,
                                              self.max_k), "sa_engine_create")
         self._h = h
-        self._pinned = []
         self._inflight = {}
         capi.check(self.lib.sa_corpus_bind(self._h, self.rows.data_ptr(), self.inv_norm.data_ptr(), 0),
                    "sa_corpus_bind")
 
     # ------------------------------------------------------------------ lifecycle
     def close(self) -> None:
+        """Destroy the engine.  Page-locked arrays handed out by ``pinned_array`` are NOT freed here: each is released
+        when its last numpy view is garbage-collected, so a caller still holding one never touches freed memory."""
         if getattr(self, "_h", None):
             self.lib.sa_engine_destroy(self._h)
             self._h = None
-            for p in self._pinned:
-                self.lib.sa_host_free(p)
-            self._pinned = []
 
     def __del__(self):  # pragma: no cover
         try:
@@ -223,12 +236,39 @@ class VectorIndex:
     def pinned_array(self, shape, dtype=np.float32) -> np.ndarray:
         """A page-locked numpy array (sa_host_alloc): passing such buffers to ``search_host`` lets the engine DMA
         them directly instead of staging through its own pinned copy.  Freed when the index is closed."""
-        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
-        p = C.c_void_p()
-        capi.check(self.lib.sa_host_alloc(C.byref(p), max(nbytes, 1)), "sa_host_alloc")
-        self._pinned.append(p)
-        buf = (C.c_char * nbytes).from_address(p.value)
-        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+        return pinned_array(shape, dtype)
+
+    def search_hits(self, q: torch.Tensor, k: int, row_offset: int = 0) -> torch.Tensor:
+        """This shard's results in exchange format: uint8 CUDA tensor [nq, k, 16] = sa_hit {cosine f64, global row i64}
+        (``hits.view(torch.float64)[..., 0]`` / ``.view(torch.int64)[..., 1]``)."""
+        assert q.is_cuda and q.dtype == torch.bfloat16 and q.dim() == 2 and q.shape[1] == self.dim
+        q = q.contiguous()
+        hits = torch.empty((q.shape[0], k, 16), dtype=torch.uint8, device=q.device)
+        capi.check(self.lib.sa_search_hits(self._h, q.data_ptr(), q.shape[0], k, int(row_offset), hits.data_ptr(),
+                                           self._stream()), "sa_search_hits")
+        return hits
+
+    def merge_hits(self, hits_all: torch.Tensor):
+        """hits_all: uint8 [n_shards, nq, k, 16] gathered from all shards.  Returns (score f32 [nq,k], global row i64)."""
+        g, nq, k, _ = hits_all.shape
+        score = torch.empty((nq, k), dtype=torch.float32, device=hits_all.device)
+        idx = torch.empty((nq, k), dtype=torch.int64, device=hits_all.device)
+        capi.check(self.lib.sa_merge_hits(self._h, hits_all.contiguous().data_ptr(), g, nq, k, score.data_ptr(),
+                                          idx.data_ptr(), self._stream()), "sa_merge_hits")
+        return score, idx
+
+    def scan_profile(self) -> dict:
+        """Per-CTA role counters of the last scan launch run with option "profile" = 1 (SM cycles): how long the TMA
+        producer waited for a free smem slot, the MMA issuer for data / for the epilogue, the epilogue for the MMA, and
+        how long the epilogue worked.  Arrays are indexed by CTA."""
+        n = self.info("last_grid")
+        a = np.zeros((n, 8), dtype=np.int64)
+        got = C.c_int()
+        capi.check(self.lib.sa_scan_profile(self._h, a.ctypes.data, n, C.byref(got)), "sa_scan_profile")
+        a = a[:got.value]
+        names = ("prod_wait_empty", "mma_wait_full", "mma_wait_tempty", "epi_wait_tfull", "epi_busy", "epi_slow_chunks",
+                 "total", "tiles")
+        return {nm: a[:, i] for i, nm in enumerate(names)}
 
     def merge_shards(self, score64_all: torch.Tensor, gidx_all: torch.Tensor):
         """score64_all / gidx_all: [n_shards, nq, k] (float64 / int64 global rows) gathered from all ranks.

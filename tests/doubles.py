@@ -36,6 +36,20 @@ class OracleIndex:
         out = (torch.from_numpy(s.astype(np.float32)), torch.from_numpy(i.astype(np.int32)))
         return out + (torch.from_numpy(s),) if want_score64 else out
 
+    # exchange-format API (sa_hit = {cosine f64, global row i64}) used by sharded.ShardedIndex
+    def search_hits(self, q, k, row_offset=0):
+        s, i = bf.cosine_topk_f64(bf.f32_to_bf16_bits(q.float().numpy()), self.bits, k)
+        hits = np.zeros(s.shape, dtype=np.dtype([("score", "<f8"), ("row", "<i8")]))
+        hits["score"] = s
+        hits["row"] = np.where(i >= 0, i.astype(np.int64) + row_offset, -1)
+        return torch.from_numpy(hits.view(np.uint8).reshape(s.shape[0], k, 16).copy())
+
+    def merge_hits(self, hits_all):
+        g, nq, k, _ = hits_all.shape
+        h = hits_all.contiguous().numpy().view(np.dtype([("score", "<f8"), ("row", "<i8")])).reshape(g, nq, k)
+        s, i = bf.merge_shard_topk([h["score"][j] for j in range(g)], [h["row"][j] for j in range(g)], [0] * g, k)
+        return torch.from_numpy(s.astype(np.float32)), torch.from_numpy(i)
+
     def merge_shards(self, all_s, all_i):
         g = all_s.shape[0]
         s, i = bf.merge_shard_topk([all_s[j].numpy() for j in range(g)], [all_i[j].numpy() for j in range(g)],

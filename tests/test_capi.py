@@ -67,42 +67,40 @@ def test_missing_library_raises(monkeypatch, tmp_path):
         capi.load()
 
 
-def plan(lib, num_sms, nq, cg, num_tiles, cap=0, qpu2=0):
-    out = (C.c_int * (5 * 16))()
+def plan(lib, num_sms, nq, cg, num_tiles, cap=0):
+    out = (C.c_int * (4 * 16))()
     n = C.c_int()
-    rc = lib.sa_debug_plan(num_sms, nq, cg, num_tiles, cap, qpu2, out, 16, C.byref(n))
+    rc = lib.sa_debug_plan(num_sms, nq, cg, num_tiles, cap, out, 16, C.byref(n))
     assert rc == 0, lib.sa_last_error()
-    return [tuple(out[5 * i + j] for j in range(5)) for i in range(n.value)]
+    return [tuple(out[4 * i + j] for j in range(4)) for i in range(n.value)]
 
 
 @pytest.mark.parametrize("cg", [1, 2])
-@pytest.mark.parametrize("qpu2", [0, 1])
 @pytest.mark.parametrize("nq", [1, 37, 128, 129, 256, 700, 1024, 1100, 4096, 5000])
 @pytest.mark.parametrize("num_tiles", [0, 1, 5, 79, 39063])
-def test_launch_planner_invariants(lib, cg, qpu2, nq, num_tiles):
+@pytest.mark.parametrize("sms", [148, 160])
+def test_launch_planner_invariants(lib, cg, nq, num_tiles, sms):
     """Host logic of the scan: every query is covered exactly once, a launch never needs more CTAs than SMs,
-    tile lanes never outnumber tiles, and the whole machine is used when the batch allows it."""
-    sms = 148
-    launches = plan(lib, sms, nq, cg, num_tiles, qpu2=qpu2)
+    tile lanes never outnumber tiles nor the merge kernel's 148-lane table, and the machine is used when the batch
+    allows it."""
+    launches = plan(lib, sms, nq, cg, num_tiles)
     rows = 128 * cg
     nxt = 0
-    for q0, n, nqb, tl, qpu in launches:
+    for q0, n, nqb, tl in launches:
         assert q0 == nxt and n > 0 and q0 % rows == 0
-        assert nqb == (n + rows - 1) // rows and tl >= 1 and qpu in (1, 2) and (qpu2 or qpu == 1)
-        nslots = (nqb + qpu - 1) // qpu
-        assert nslots * tl * cg <= sms and tl <= max(num_tiles, 1)
+        assert nqb == (n + rows - 1) // rows and tl >= 1
+        assert nqb * tl * cg <= sms and tl <= max(num_tiles, 1) and tl <= 148
         nxt += n
     assert nxt == nq
     if num_tiles >= 148 and nq >= rows:
-        used = max(((nqb + qpu - 1) // qpu) * tl * cg for _, _, nqb, tl, qpu in launches)
-        assert used >= 0.85 * sms, launches
+        used = max(nqb * tl * cg for _, _, nqb, tl in launches)
+        assert used >= 0.85 * 148, launches
 
 
 def test_launch_planner_headline_shapes(lib):
-    assert plan(lib, 148, 1024, 2, 39063) == [(0, 1024, 4, 18, 1)]           # 4 pair blocks x 18 lanes = 72 pairs
-    assert plan(lib, 148, 1024, 2, 39063, qpu2=1) == [(0, 1024, 4, 37, 2)]   # 2 slots x 37 lanes = all 74 pairs
-    assert plan(lib, 148, 128, 1, 39063) == [(0, 128, 1, 148, 1)]            # HBM-bound: every SM its own lane
-    assert plan(lib, 148, 512, 2, 39063) == [(0, 512, 2, 37, 1)]             # already fills the machine
-    p = plan(lib, 148, 4096, 2, 4883)                                        # config 4 per GPU: 2 launches of 8 x 9
-    assert [x[2:] for x in p] == [(8, 9, 1), (8, 9, 1)]
-    assert len(plan(lib, 148, 1100, 2, 118, cap=2)) == 3                     # forced small launches
+    assert plan(lib, 148, 1024, 2, 39063) == [(0, 1024, 4, 18)]             # 4 pair blocks x 18 lanes = 72 pairs
+    assert plan(lib, 148, 128, 1, 39063) == [(0, 128, 1, 148)]              # HBM-bound: every SM its own lane
+    assert plan(lib, 148, 512, 2, 39063) == [(0, 512, 2, 37)]               # already fills the machine
+    p = plan(lib, 148, 4096, 2, 4883)                                       # config 4 per GPU: 2 launches of 8 x 9
+    assert [x[2:] for x in p] == [(8, 9), (8, 9)]
+    assert len(plan(lib, 148, 1100, 2, 118, cap=2)) == 3                    # forced small launches

