@@ -86,6 +86,7 @@ struct DeviceGuard {
   if (_dg.rc != cudaSuccess) return fail(SA_ERR_CUDA, "cudaSetDevice(%d) failed: %s", (dev), cudaGetErrorString(_dg.rc))
 
 constexpr int kMaxLaunches = 16;
+constexpr int kDefaultL2Prefetch = 0;  // set from the sweep in tools/gpu_sweep.py (profiles/)
 constexpr int kTimingRing = 16;
 constexpr int kHostSlots = SA_HOST_SLOTS;
 
@@ -159,6 +160,7 @@ struct sa_engine {
   int opt_pace_max = -1;   // -1 = auto (8 x gain)
   int opt_unit_map = 0;
   int opt_list_len = 0;    // 0 = auto (16 when k <= 12, else 32)
+  int opt_l2_prefetch = -1; // K slices the scan's L2 prefetch stream runs ahead (-1 = auto, 0 = off)
   int opt_force_fix = 0;   // test hook: every (query, lane) goes through the exact fallback scan
   int64_t last_fix_entries = -1;  // option "count_fix": work-queue length of the last search (costs a host sync)
   int opt_count_fix = 0;
@@ -367,6 +369,7 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
     sp.part_idx = e->part_idx;
     sp.part_drop = e->part_drop;
     sp.corpus_evict_first = (lp.nqb == 1) ? 1 : 0;  // a tile nobody else will ask for: stream it through L2
+    sp.l2_prefetch = e->opt_l2_prefetch >= 0 ? e->opt_l2_prefetch : kDefaultL2Prefetch;
     sp.lane_progress = nullptr;
     sp.max_drift = e->opt_max_drift >= 0 ? e->opt_max_drift : 1;
     sp.pace_gain = 0;
@@ -1274,6 +1277,11 @@ int sa_set_option(sa_engine* e, const char* name, int64_t value) {
   if (!strcmp(name, "max_launch_qblocks")) {
     if (value < 0) return fail(SA_ERR_ARG, "max_launch_qblocks must be >= 0");
     e->opt_max_launch_qblocks = static_cast<int>(value);
+    return SA_OK;
+  }
+  if (!strcmp(name, "l2_prefetch")) {
+    if (value < -1 || value > 256) return fail(SA_ERR_ARG, "l2_prefetch must be in [-1, 256]");
+    e->opt_l2_prefetch = static_cast<int>(value);
     return SA_OK;
   }
   if (!strcmp(name, "force_fix")) {

@@ -75,6 +75,7 @@ struct ScanParams {
   int* part_idx;          // [gridDim.x][128][kKL]
   float* part_drop;       // [gridDim.x][128]  upper bound on the approximate score of the lane's rows not in the list
   int corpus_evict_first; // 1: corpus tiles are read by a single query block -> stream them through L2
+  int l2_prefetch;        // K slices the L2 prefetch stream runs ahead of the smem ring's TMA loads (0 = off)
   int* lane_progress;     // [tl_count][nqb] tiles whose loads each unit has issued (zero at launch), or nullptr
   int unit_map;           // 0: unit = tl*nqb + qb (lane-mates adjacent), 1: unit = qb*TL + tl (lane-mates TL apart)
   int max_drift;          // lead (in tiles) over the slowest lane-mate that is not paced
@@ -398,6 +399,18 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             const long long c0 = clock64();
             while (clock64() - c0 < pace) {
             }
+          }
+          if (p.l2_prefetch > 0) {
+            // The smem ring holds 4 (6) K slices; HBM latency under load is longer than the ring lasts, so the ring
+            // alone leaves the MMA issuer starved while the producer waits for free slots.  Ask L2 for the slice
+            // `l2_prefetch` positions ahead: when its turn in the ring comes, the TMA load is an L2 hit.
+            int kb2 = kb + p.l2_prefetch, t2 = t;
+            while (kb2 >= p.num_kb) {
+              kb2 -= p.num_kb;
+              t2 += TL;
+            }
+            if (t2 < p.num_tiles)
+              tma_prefetch_l2_2d(&tmap_c, kb2 * kBlockK, t2 * kBlockN + static_cast<int>(rank) * Cfg::kBRows);
           }
           if constexpr (kCG == 1) {
             mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);

@@ -34,12 +34,18 @@ def _worker(rank, world, port, out_dir):
         dist.all_gather(buf, torch.full((4,), float(rank)))
         calls[0] += 1
 
-    def reduce_max(flag):
-        t = torch.tensor([flag], dtype=torch.int32)
+    def reduce_max(flags):
+        t = torch.tensor(flags, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return int(t.item())
+        return t.tolist()
 
-    n = bench.collective_preheat(step, 0.25, world, lambda: None, reduce_max)
+    t0 = time.perf_counter()
+
+    def stop_flags():                             # per-rank opinions differ: rank 0 is "stable" early, rank 1 never is
+        el = time.perf_counter() - t0
+        return (rank == 0 and el > 0.05), el > (0.25 if rank == 0 else 0.30)
+
+    n, secs = bench.collective_preheat(step, lambda: None, stop_flags, world, reduce_max)
     for _ in range(3):                            # "warm-up + timed" steps afterwards must still pair up
         step()
     dist.barrier()
@@ -55,7 +61,7 @@ def test_preheat_runs_the_same_number_of_collective_steps_on_every_rank(tmp_path
     assert r[0] == r[1] and r[0]["n"] >= 4 and r[0]["calls"] == r[0]["n"] + 3
 
 
-def test_preheat_single_rank_and_disabled():
+def test_preheat_single_rank_stops_on_stable_or_timeout():
     sys.path.insert(0, ROOT)
     import bench
     calls = [0]
@@ -63,9 +69,38 @@ def test_preheat_single_rank_and_disabled():
     def step():
         calls[0] += 1
         time.sleep(0.001)
-    assert bench.collective_preheat(step, 0.0, 1, lambda: None) == 0 and calls[0] == 0
-    n = bench.collective_preheat(step, 0.05, 1, lambda: None)
-    assert n == calls[0] and n % 4 == 0 and n >= 4
+    n, _ = bench.collective_preheat(step, lambda: None, lambda: (True, False), 1)
+    assert n == calls[0] == 4                                             # stable at once: one chunk
+    t0 = time.perf_counter()
+    n, secs = bench.collective_preheat(step, lambda: None, lambda: (False, time.perf_counter() - t0 > 0.05), 1)
+    assert n % 4 == 0 and n >= 8 and secs >= 0.05                         # never stable: runs into the time limit
+
+
+def test_host_data_pool_generates_canonical_chunks_and_the_parallel_oracle_equals_the_definition():
+    """bench.py's worker pool: (i) what it writes into the shared mapping IS oracle.synth_rows chunk by chunk, also when a
+    shard boundary cuts a chunk; (ii) its parallel oracle (per-piece fp32 prefilter + float64 re-scoring) returns exactly
+    what the oracle's definition returns."""
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import bench
+    from oracle import bruteforce as bf
+    old = bench.CHUNK
+    bench.CHUNK = 1000                                                    # small chunks keep this a CPU-seconds test
+    try:
+        dim, n_total, lo, hi = 64, 3500, 700, 3500                        # rows 700..3499: cuts chunk 0, ragged last chunk
+        host = bench.HostData((hi - lo) * dim * 2, 3)
+        seen = []
+        host.generate(77, dim, lo, hi, n_total, lambda first, n: seen.append((first, n)))
+        shard = host.view(hi - lo, dim).copy()
+        want = np.concatenate([bf.synth_rows(77, c, min(1000, n_total - c * 1000), dim) for c in range(4)])[lo:hi]
+        assert (shard == want).all() and sorted(seen) == [(0, 300), (300, 1000), (1300, 1000), (2300, 500)]
+        q = bf.synth_queries(78, 9, dim, want[:1000])
+        rs, ri = host.oracle_topk(q, hi - lo, dim, 10)
+        host.close()
+        es, ei = bf.cosine_topk_f64(q, want, 10)
+        assert (ri == ei).all() and np.abs(rs - es).max() < 1e-15
+    finally:
+        bench.CHUNK = old
 
 
 def test_reference_arm_prints_the_contract_line():
