@@ -211,9 +211,40 @@ class HostData:
         self.pool.join()
 
 
-def auto_workers(world):
+def host_memory_available():
+    """Bytes this process may still use: MemAvailable, capped by the cgroup limit when there is one."""
+    avail = None
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable:"):
+                    avail = int(line.split()[1]) * 1024
+    except OSError:
+        pass
+    for lim_p, cur_p in (("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory.current"),
+                         ("/sys/fs/cgroup/memory/memory.limit_in_bytes", "/sys/fs/cgroup/memory/memory.usage_in_bytes")):
+        try:
+            lim = open(lim_p).read().strip()
+            if lim != "max" and int(lim) < (1 << 60):
+                room = int(lim) - int(open(cur_p).read().strip())
+                avail = room if avail is None else min(avail, room)
+        except (OSError, ValueError):
+            pass
+    return avail if avail is not None else 64 << 30
+
+
+WORKER_PEAK_BYTES = 3 << 30      # one canonical chunk in fp32 (1.6 GB) + its bf16 copy + slack
+
+
+def auto_workers(world, shared_bytes=0, mem_avail=None):
+    """Worker processes per rank: bounded by the cores AND by memory -- every worker holds a whole 262144 x dim fp32
+    chunk while it generates it, and the shared host copy of the shard has to fit beside them (a first version of this
+    pool took a GPU box down by running 48 workers x 10 GB)."""
     n = os.cpu_count() or 8
-    return max(2, min(48, (n - 2 * world) // max(world, 1)))
+    by_cpu = max(2, min(32, (n - 2 * world) // max(world, 1)))
+    mem = (host_memory_available() if mem_avail is None else mem_avail) // max(world, 1)
+    by_mem = int((0.6 * mem - shared_bytes) // WORKER_PEAK_BYTES)
+    return max(1, min(by_cpu, by_mem))
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -298,7 +329,7 @@ def run_reference(a):
         return
     from oracle import bruteforce as bf
     nq, rows = a.cpu_sample_queries, a.cpu_sample_rows
-    host = HostData(rows * a.dim * 2, min(auto_workers(1), max(2, (rows + CHUNK - 1) // CHUNK)))
+    host = HostData(rows * a.dim * 2, min(auto_workers(1, rows * a.dim * 2), max(2, (rows + CHUNK - 1) // CHUNK)))
     host.generate(a.seed, a.dim, 0, rows, rows)
     host.close()
     shard = host.view(rows, a.dim)
@@ -684,10 +715,20 @@ def run_b200(a):
     n5_total, dim5 = 50_000_000, 768
     lo5, hi5 = rank * n5_total // world, (rank + 1) * n5_total // world
     shared_bytes = n_local * dim * 2
+    mem_avail = host_memory_available()
+    notes = []
+    if "cfg5" in extras and 0.6 * mem_avail / world < (hi5 - lo5) * dim5 * 2 + 2 * WORKER_PEAK_BYTES:
+        extras.remove("cfg5")        # every rank decides alike: same box, same arithmetic
+        notes.append(f"cfg5 skipped: its host copy ({(hi5 - lo5) * dim5 * 2 / 2**30:.0f} GiB per rank) does not fit in the "
+                     f"{mem_avail / 2**30:.0f} GiB of host memory available")
     if "cfg5" in extras:
         shared_bytes = max(shared_bytes, (hi5 - lo5) * dim5 * 2)
+    if 0.6 * mem_avail / world < shared_bytes + WORKER_PEAK_BYTES:
+        raise SystemExit(f"bench.py needs {shared_bytes / 2**30:.0f} GiB of host memory per rank for the canonical corpus copy; "
+                         f"{mem_avail / 2**30:.0f} GiB available for {world} rank(s)")
     # ---- host side first: the worker pool is forked before CUDA exists in this process
-    host = HostData(shared_bytes, a.workers or auto_workers(world))
+    n_workers = a.workers or auto_workers(world, shared_bytes, mem_avail)
+    host = HostData(shared_bytes, n_workers)
 
     import torch
     import torch.distributed as dist
@@ -760,7 +801,8 @@ def run_b200(a):
                        "l2": "inputs larger than L2 (corpus shard %.1f GB per batch)" % (n_local * dim * 2 / 1e9),
                        "cta_group": a.cta_group or "auto", "preheat": "until the SM clock is stable for 1 s "
                        f"(<= {a.preheat_max} s): {m['preheat_s']:.1f} s, {m['preheat_batches']} batches",
-                       "data_generation_s": gen_s},
+                       "data_generation_s": gen_s, "host": {"workers": n_workers, "mem_available_gib": mem_avail / 2**30,
+                                                            "notes": notes}},
             "e2e": m["e2e"], "gpu_launches": int(m["gpu_launches_per_batch"] * nb_total),
             "clocks": m["clocks"], "clocks_whole_region": m["clocks_whole_region"], "roofline": m["roofline"],
         }

@@ -52,14 +52,25 @@ CHUNK_ROWS = 262_144  # generation chunk of the synthetic corpora (SURVEY.md sec
 # bf16 <-> fp32 (bit patterns as uint16)
 # --------------------------------------------------------------------------------------------------
 def f32_to_bf16_bits(x: np.ndarray) -> np.ndarray:
-    """Round-to-nearest-even fp32 -> bf16, returned as uint16 bit patterns (NaN stays NaN)."""
+    """Round-to-nearest-even fp32 -> bf16, returned as uint16 bit patterns (NaN stays NaN).
+    Works in 32-bit arithmetic over blocks of ~4M elements, so a 262144 x 1536 chunk needs no multi-GB temporaries
+    (u + 0x7FFF + lsb cannot wrap for a non-NaN input: the largest finite/inf pattern is 0xFF800000)."""
     x = np.ascontiguousarray(x, dtype=np.float32)
-    u = x.view(np.uint32)
-    r = ((u.astype(np.uint64) + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint16)
-    nan = (u & 0x7FFFFFFF) > 0x7F800000
-    if nan.any():
-        r = np.where(nan, ((u >> 16) | 0x40).astype(np.uint16), r)
-    return r
+    u = x.view(np.uint32).reshape(-1)
+    r = np.empty(u.shape, dtype=np.uint16)
+    step = 1 << 22
+    for lo in range(0, u.size, step):
+        b = u[lo:lo + step]
+        t = (b >> 16) & 1
+        t += 0x7FFF
+        nan = (b & 0x7FFFFFFF) > 0x7F800000
+        with np.errstate(over="ignore"):
+            t += b                                  # wraps only where `nan` is set; those are overwritten below
+        out = (t >> 16).astype(np.uint16)
+        if nan.any():
+            out[nan] = ((b[nan] >> 16) | 0x40).astype(np.uint16)
+        r[lo:lo + step] = out
+    return r.reshape(x.shape)
 
 
 def bf16_bits_to_f32(b: np.ndarray) -> np.ndarray:

@@ -29,6 +29,19 @@ int fail(int rc, const char* fmt, ...) {
   return rc;
 }
 
+}  // namespace
+
+// used by the other translation units of the library (sa_wire.cpp); not part of the public headers
+extern "C" int sa_internal_fail(int rc, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return rc;
+}
+
+namespace {
+
 #define SA_CUDA(call)                                                                                \
   do {                                                                                               \
     cudaError_t _e = (call);                                                                         \

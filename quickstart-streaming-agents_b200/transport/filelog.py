@@ -131,6 +131,42 @@ class _Partition:
             finally:
                 fcntl.flock(lf, fcntl.LOCK_UN)
 
+    def append_framed(self, data, rel_positions) -> int:
+        """Append records that are ALREADY in the log's framing (one buffer, e.g. from sa_wire_encode_*):
+        rel_positions[i] is the offset of record i inside `data`.  Returns the first offset written."""
+        self.create()
+        with open(self.log_path, "ab") as lf, open(self.idx_path, "ab") as xf:
+            fcntl.flock(lf, fcntl.LOCK_EX)
+            try:
+                lf.seek(0, os.SEEK_END)
+                xf.seek(0, os.SEEK_END)
+                first = xf.tell() // 8
+                pos = lf.tell()
+                lf.write(data)
+                lf.flush()
+                import numpy as np
+                xf.write((np.asarray(rel_positions, dtype="<u8") + np.uint64(pos)).tobytes())
+                xf.flush()
+                return first
+            finally:
+                fcntl.flock(lf, fcntl.LOCK_UN)
+
+    def read_raw(self, offset: int, max_records: int):
+        """Records [offset, offset+n) that exist right now as ONE byte string in the log's framing (to be split by
+        sa_wire_split_log): returns (n, bytes).  No per-record Python objects are created."""
+        hi = self.high()
+        if offset >= hi:
+            return 0, b""
+        n = min(max_records, hi - offset)
+        with open(self.idx_path, "rb") as xf:
+            xf.seek(offset * 8)
+            raw = xf.read((n + 1) * 8)            # one position past the slice, if it exists, bounds the read
+        positions = struct.unpack(f"<{len(raw) // 8}Q", raw)
+        with open(self.log_path, "rb") as lf:
+            lf.seek(positions[0])
+            data = lf.read(positions[n] - positions[0]) if len(positions) > n else lf.read()
+        return n, data
+
     def read(self, offset: int, max_records: int):
         """Messages [offset, offset+max_records) that exist right now."""
         hi = self.high()
@@ -234,6 +270,12 @@ class Producer:
         if sum(len(v) for v in self._pending.values()) >= 4096:
             self.flush()
 
+    def produce_framed(self, topic, data, rel_positions, partition=0) -> int:
+        """Append a batch of records that were framed natively (sa_wire_encode_*) with one write.  Records produced
+        earlier on this producer are flushed first, so the topic keeps the producer's order."""
+        self.flush()
+        return self.broker.partition(topic, int(partition)).append_framed(data, rel_positions)
+
     def poll(self, timeout=0):
         return 0
 
@@ -277,7 +319,7 @@ class Consumer:
                 if (t, p) in self._pos:
                     continue
                 lo, hi = self.broker.get_watermark_offsets(TopicPartition(t, p))
-                start = committed.get(f"{t}-{p}")
+                start = None if t in getattr(self, "_ignore_committed", ()) else committed.get(f"{t}-{p}")
                 if start is None:
                     start = lo if self.reset == "earliest" else hi
                 self._pos[(t, p)] = max(int(start), lo)
@@ -304,6 +346,42 @@ class Consumer:
         if out and self.auto_commit:
             self.commit()
         return out
+
+    def consume_raw(self, num_messages=1):
+        """Batch form without per-record objects: up to num_messages records of ONE partition as
+        (topic, partition, first_offset, n, bytes in the log's framing), or None when nothing is pending."""
+        self._assign()
+        keys = sorted(self._pos)
+        for i in range(len(keys)):
+            tp = keys[(self._rr + i) % len(keys)]
+            n, data = self.broker.partition(*tp).read_raw(self._pos[tp], num_messages)
+            if n:
+                first = self._pos[tp]
+                self._pos[tp] = first + n
+                self._rr += 1
+                return tp[0], tp[1], first, n, data
+        self._rr += 1
+        return None
+
+    def commit_upto(self, topic: str, partition: int, next_offset: int) -> None:
+        """Commit `next_offset` as the group's position of one partition (pipelined stages commit batch by batch)."""
+        self.broker.commit(self.group, {f"{topic}-{partition}": int(next_offset)})
+
+    def seek(self, tp: TopicPartition) -> None:
+        """Continue reading `tp.topic`/`tp.partition` at `tp.offset` (clamped to the low watermark), whatever the
+        group has committed."""
+        lo, _ = self.broker.get_watermark_offsets(tp)
+        self._pos[(tp.topic, tp.partition)] = max(int(tp.offset), lo)
+
+    def seek_to_beginning(self, topic: str) -> None:
+        """Re-read `topic` from the low watermark of every partition (a consumer whose state is rebuilt from the log)."""
+        for p in self.broker.list_topics().get(topic, []):
+            self.seek(TopicPartition(topic, p, 0))
+        self._ignore_committed = getattr(self, "_ignore_committed", set()) | {topic}
+
+    def positions(self, topic: str) -> dict[int, int]:
+        self._assign()
+        return {p: o for (t, p), o in self._pos.items() if t == topic}
 
     def poll(self, timeout=0.0):
         msgs = self.consume(1, timeout)

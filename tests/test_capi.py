@@ -14,9 +14,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def header_functions():
-    src = open(os.path.join(ROOT, "include", "sa_api.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(sa_[a-z0-9_]+)\s*\(", src)))
+    names = set()
+    for h in ("sa_api.h", "sa_wire.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(sa_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
 
 
 def test_header_and_binding_agree():

@@ -26,7 +26,8 @@ if __name__ == "__main__":
     t = VectorTable(NullIndex()); t.load_columns([f"d{i}" for i in range(1000)], ["chunk text " * 20] * 1000)
     if gpu:   # the real engine over a 1M x 1536 corpus: QPS_e2e of the search stage over the file-log transport
         import torch
-        from bench import fill_corpus
+        from tools.gpu_prof import fill as _fill
+        fill_corpus = lambda ix, rows, dim, seed: _fill(ix, rows, dim, seed)
         from qsa_b200.engine import VectorIndex
         rows = 1_000_000
         ix = VectorIndex(dim=1536, capacity=rows, max_batch=1024, max_k=3)
