@@ -139,7 +139,14 @@ class VectorIndex:
         n = len(self)
         torch.cuda.current_stream(self.device).synchronize()
         bits = self.rows[:n].view(torch.int16).cpu().numpy().view(np.uint16)
-        np.savez(path, rows=bits, inv_norm=self.inv_norm[:n].cpu().numpy(), dim=np.int64(self.dim))
+        import os
+        path = path if path.endswith(".npz") else path + ".npz"
+        tmp = path + ".tmp"
+        with open(tmp, "wb") as f:                       # written under a temporary name, then renamed: never half a file
+            np.savez(f, rows=bits, inv_norm=self.inv_norm[:n].cpu().numpy(), dim=np.int64(self.dim))
+            f.flush()
+            os.fsync(f.fileno())
+        os.replace(tmp, path)
         return n
 
     def restore(self, path: str) -> int:

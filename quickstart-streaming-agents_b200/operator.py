@@ -36,6 +36,36 @@ def _avro_nullable_string(v: str | None) -> bytes:
     return bytes(out) + raw
 
 
+class ByteArena:
+    """Append-only arena of byte strings with an offsets table (value i = data[off[i]:off[i+1]]), kept in numpy
+    arrays so the native encoder (sa_wire_encode_search_results) can read it in place."""
+
+    def __init__(self):
+        self.data = np.zeros(1 << 16, dtype=np.uint8)
+        self.off = np.zeros(1 << 10, dtype=np.uint64)
+        self.n = 0
+        self.used = 0
+
+    def append(self, b: bytes) -> None:
+        need = self.used + len(b)
+        if need > self.data.size:
+            grown = np.zeros(max(need, 2 * self.data.size), dtype=np.uint8)
+            grown[:self.used] = self.data[:self.used]
+            self.data = grown
+        if self.n + 2 > self.off.size:
+            grown = np.zeros(2 * self.off.size, dtype=np.uint64)
+            grown[:self.n + 1] = self.off[:self.n + 1]
+            self.off = grown
+        self.data[self.used:need] = np.frombuffer(b, dtype=np.uint8)
+        self.used = need
+        self.n += 1
+        self.off[self.n] = need
+
+    def clear(self) -> None:
+        self.n = 0
+        self.used = 0
+
+
 @dataclass
 class SearchHit:
     document_id: str | None
@@ -58,6 +88,18 @@ class VectorTable:
         # search_results record is then a concatenation of ready-made byte strings (pipeline/serve.py fast path)
         self.avro_document_id: list[bytes] = []
         self.avro_chunk: list[bytes] = []
+        # ... and the same bytes in arenas, for the native batch encoder (sa_wire_encode_search_results)
+        self.arena_document_id = ByteArena()
+        self.arena_chunk = ByteArena()
+        # offsets of the source topic (documents_embed) up to which this table's content is complete; restored by load()
+        self.source_offsets: dict[str, int] | None = None
+
+    def _push_avro(self, document_id, chunk) -> None:
+        d, c = _avro_nullable_string(document_id), _avro_nullable_string(chunk)
+        self.avro_document_id.append(d)
+        self.avro_chunk.append(c)
+        self.arena_document_id.append(d)
+        self.arena_chunk.append(c)
 
     def __len__(self) -> int:
         return len(self.document_id)
@@ -81,8 +123,7 @@ class VectorTable:
             self.document_id.append(document_ids[i])
             self.chunk.append(chunks[i])
             self.metadata.append(metadata[i])
-            self.avro_document_id.append(_avro_nullable_string(document_ids[i]))
-            self.avro_chunk.append(_avro_nullable_string(chunks[i]))
+            self._push_avro(document_ids[i], chunks[i])
             if document_ids[i] is not None:
                 self._row_of[document_ids[i]] = first + j
 
@@ -97,38 +138,80 @@ class VectorTable:
             self.document_id.append(d)
             self.chunk.append(c)
             self.metadata.append(m)
-            self.avro_document_id.append(_avro_nullable_string(d))
-            self.avro_chunk.append(_avro_nullable_string(c))
+            self._push_avro(d, c)
 
-    def save(self, directory: str) -> int:
-        """Checkpoint: the index snapshot (if the index supports it) + the side table as JSON lines."""
+    def save(self, directory: str, source_offsets: dict[str, int] | None = None) -> int:
+        """Checkpoint: the index snapshot (if the index supports it), the side table as JSON lines, and LAST a manifest
+        naming both (generation-numbered files, each written to a temporary name and renamed), so a crash at any point
+        leaves the previous checkpoint intact and readable.  ``source_offsets`` ({"<topic>-<partition>": next offset})
+        records how far into its source topic the table's content reaches: a resumed sink continues exactly there."""
         import json
         import os
         os.makedirs(directory, exist_ok=True)
+        prev = self._read_manifest(directory)
+        gen = (prev["generation"] + 1) if prev else 1
+        n = len(self)
+        files = {"columns": f"columns.{gen}.jsonl"}
         if hasattr(self.index, "snapshot"):
-            self.index.snapshot(os.path.join(directory, "index.npz"))
-        tmp = os.path.join(directory, "columns.jsonl.tmp")
+            files["index"] = f"index.{gen}.npz"
+            self.index.snapshot(os.path.join(directory, files["index"]))          # atomic (tmp + rename) in the index
+        tmp = os.path.join(directory, files["columns"] + ".tmp")
         with open(tmp, "w", encoding="utf-8") as f:
             for d, c, m in zip(self.document_id, self.chunk, self.metadata):
                 f.write(json.dumps({"document_id": d, "chunk": c, "metadata": m}, ensure_ascii=False) + "\n")
-        os.replace(tmp, os.path.join(directory, "columns.jsonl"))
-        return len(self)
+            f.flush()
+            os.fsync(f.fileno())
+        os.replace(tmp, os.path.join(directory, files["columns"]))
+        man = {"generation": gen, "rows": n, "files": files, "source_offsets": source_offsets or {}}
+        tmp = os.path.join(directory, "manifest.json.tmp")
+        with open(tmp, "w") as f:
+            json.dump(man, f)
+            f.flush()
+            os.fsync(f.fileno())
+        os.replace(tmp, os.path.join(directory, "manifest.json"))
+        if prev:                                                                  # the old generation is garbage now
+            for name in prev["files"].values():
+                try:
+                    os.remove(os.path.join(directory, name))
+                except OSError:
+                    pass
+        return n
+
+    @staticmethod
+    def _read_manifest(directory: str):
+        import json
+        import os
+        try:
+            with open(os.path.join(directory, "manifest.json")) as f:
+                return json.load(f)
+        except (OSError, ValueError):
+            return None
+
+    @classmethod
+    def has_checkpoint(cls, directory: str) -> bool:
+        return cls._read_manifest(directory) is not None
 
     def load(self, directory: str) -> int:
-        """Resume from ``save``: restores the index and the side table (must be called on an empty table)."""
+        """Resume from ``save``: restores the index, the side table and ``source_offsets`` (call on an empty table)."""
         import json
         import os
         assert len(self) == 0, "load() needs an empty table"
+        man = self._read_manifest(directory)
+        if man is None:
+            raise FileNotFoundError(f"no checkpoint manifest in {directory}")
         rows = []
-        with open(os.path.join(directory, "columns.jsonl"), encoding="utf-8") as f:
+        with open(os.path.join(directory, man["files"]["columns"]), encoding="utf-8") as f:
             for line in f:
                 rows.append(json.loads(line))
-        if hasattr(self.index, "restore"):
-            n = self.index.restore(os.path.join(directory, "index.npz"))
+        if len(rows) != man["rows"]:
+            raise ValueError(f"snapshot mismatch: manifest says {man['rows']} rows, columns file has {len(rows)}")
+        if hasattr(self.index, "restore") and "index" in man["files"]:
+            n = self.index.restore(os.path.join(directory, man["files"]["index"]))
             if n != len(rows):
                 raise ValueError(f"snapshot mismatch: {n} vectors, {len(rows)} column rows")
         self.load_columns([r["document_id"] for r in rows], [r["chunk"] for r in rows], [r["metadata"] for r in rows])
         # a re-published document tombstones its old row: the live row of an id is its LAST occurrence
+        self.source_offsets = dict(man.get("source_offsets") or {})
         return len(self)
 
     def clear(self) -> None:
@@ -140,6 +223,8 @@ class VectorTable:
         self._row_of.clear()
         self.avro_document_id.clear()
         self.avro_chunk.clear()
+        self.arena_document_id.clear()
+        self.arena_chunk.clear()
 
 
 def atlas_score(cosine: float) -> float:
@@ -174,7 +259,8 @@ def vector_search_agg(table: VectorTable, descriptor: str, query_vectors: np.nda
     return out
 
 
-def search_results_avro_body(table: VectorTable, query: str | None, score_row, idx_row, n: int = 3) -> bytes:
+def search_results_avro_body(table: VectorTable, query: str | None, score_row, idx_row, n: int = 3,
+                             score_mode: str = "cosine") -> bytes:
     """Avro body of one ``search_results`` record straight from a result row (scores, table rows) -- byte-identical to
     encoding ``flatten_search_results(...)`` with the generic codec, without building the dict."""
     import struct
@@ -186,7 +272,8 @@ def search_results_avro_body(table: VectorTable, query: str | None, score_row, i
         else:
             parts.append(table.avro_document_id[i])
             parts.append(table.avro_chunk[i])
-            parts.append(b"\x02" + struct.pack("<d", float(score_row[j])))
+            sc = float(score_row[j])
+            parts.append(b"\x02" + struct.pack("<d", atlas_score(sc) if score_mode == "atlas" else sc))
     return b"".join(parts)
 
 

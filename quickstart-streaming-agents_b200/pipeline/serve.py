@@ -12,9 +12,22 @@ Records on ``queries_embed`` / ``documents_embed`` may also come from outside (p
 Delivery is at-least-once: each stage commits its consumer offsets after its outputs are flushed.
 A poison record (bad magic byte, truncated Avro, wrong embedding length) is quarantined to ``<topic>.dlq``
 with the error text in its key, and the stage moves on.
+
+Durability.  The reference's vector table lives in Atlas and survives a restart of the Flink statements; here it lives
+in HBM and does not.  So the sink stage's read position is tied to the TABLE's state, never to a consumer group's
+committed offsets: a table restored from a checkpoint resumes ``documents_embed`` at the offsets stored inside that
+checkpoint, and a table that starts empty re-reads ``documents_embed`` from its low watermark (the durable log rebuilds
+it).  Every other stage resumes from its group offsets as usual.
+
+Search stage.  The hot loop works a batch at a time with no per-record Python objects: one read of the partition log
+(``consume_raw``), native split + Avro decode of the batch straight into a page-locked buffer (``sa_wire_*``), the
+two-slot host search of the C ABI, native Avro encode + log framing of the results, one append.  Records in an unusual
+shape fall back to the generic codec, record by record, inside the same batch (order is preserved).
 """
 from __future__ import annotations
 
+import ctypes as C
+import json
 import logging
 import struct
 import time
@@ -23,7 +36,7 @@ import numpy as np
 
 from ..embed.stub import StubEmbedder
 from ..operator import VectorTable, flatten_search_results, rag_prompt, search_results_avro_body, vector_search_agg
-from ..transport.filelog import Consumer, Producer
+from ..transport.filelog import Consumer, Message, Producer, TopicPartition
 from ..wire import avro, schemas
 from ..wire.registry import SchemaRegistry
 
@@ -83,13 +96,17 @@ class Codec:
 
 class Lab2Pipeline:
     def __init__(self, log_dir: str, table: VectorTable, embedder=None, k: int = 3, max_batch: int = 1024,
-                 group: str = "sa-lab2", generator=stub_generator):
+                 group: str = "sa-lab2", generator=stub_generator, score_mode: str = "cosine", native: bool | None = None,
+                 metrics_file: str | None = None, metrics_every_s: float = 5.0):
+        if score_mode not in ("cosine", "atlas"):
+            raise ValueError("score_mode must be 'cosine' (raw) or 'atlas' ((1 + cos) / 2, what MongoDB Atlas reports)")
         self.log_dir = log_dir
         self.table = table
         self.embedder = embedder or StubEmbedder(table.index.dim)
         self.k = k
         self.max_batch = max_batch
         self.generator = generator
+        self.score_mode = score_mode
         self.codec = Codec(log_dir)
         self.producer = Producer({"log.dir": log_dir})
         conf = {"log.dir": log_dir, "group.id": group, "auto.offset.reset": "earliest", "enable.auto.commit": False}
@@ -98,8 +115,33 @@ class Lab2Pipeline:
             c = Consumer(conf)
             c.subscribe([t])
             self.consumers[t] = c
+        # the sink reads from where the TABLE's content ends, not from where some earlier process committed
+        sink = self.consumers["documents_embed"]
+        if table.source_offsets:
+            sink.seek_to_beginning("documents_embed")      # partitions the checkpoint has never seen start at their beginning
+            for key, off in table.source_offsets.items():
+                t, _, p = key.rpartition("-")
+                if t == "documents_embed":
+                    sink.seek(TopicPartition(t, int(p), int(off)))
+        else:
+            sink.seek_to_beginning("documents_embed")
         self.stats = {"documents": 0, "queries": 0, "searches": 0, "responses": 0, "quarantined": 0,
-                      "search_seconds": 0.0}
+                      "search_seconds": 0.0, "search_batches": 0, "snapshots": 0}
+        # native batch codecs (include/sa_wire.h); the generic Python codec stays the reference implementation
+        self._wire = None
+        if native is None or native:
+            try:
+                from .. import capi
+                self._wire = capi.load()
+            except Exception:
+                if native:
+                    raise
+        self._qbuf = None          # two query staging buffers (page-locked when the index can DMA from them)
+        self._lat_ms: list[float] = []
+        self._metrics_file, self._metrics_every_s = metrics_file, metrics_every_s
+        self._metrics_t0 = time.time()
+        self._metrics_q0 = 0
+        self._sink_dirty = False
 
     # ------------------------------------------------------------------ helpers
     def _decode_all(self, topic: str, msgs):
@@ -156,9 +198,10 @@ class Lab2Pipeline:
         if ids:
             self.table.upsert_many(ids, chunks, np.stack(vecs), metas)
             self.stats["documents"] += len(ids)
+            self._sink_dirty = True
         if msgs:
             self.producer.flush()
-            c.commit()
+            c.commit()      # informational only: the sink's start position comes from the table (see module docstring)
         return len(msgs)
 
     def stage_queries(self) -> int:
@@ -219,32 +262,187 @@ class Lab2Pipeline:
         return texts, vecs, leftovers
 
     def _decode_batch(self, msgs):
-        """queries_embed messages -> (texts, vectors): fast batch path, generic codec (and quarantine) for the rest."""
+        """queries_embed messages -> (texts, vectors) in stream order: fast batch path, generic codec (and quarantine) for
+        the records the fast path does not take."""
         texts, vecs, leftovers = self._decode_queries_embed_fast(msgs)
-        if leftovers:
-            slow_t, slow_v = [], []
-            for m, r in self._decode_all("queries_embed", leftovers):
-                vec = r.get("embedding")
-                if self._check_vec("queries_embed", m, vec):
-                    slow_t.append(r.get("query"))
-                    slow_v.append(vec)
-            if slow_v:
-                texts = texts + slow_t
-                vecs = np.concatenate([vecs, np.stack(slow_v)]) if len(vecs) else np.stack(slow_v)
-        return texts, np.ascontiguousarray(vecs, dtype=np.float32)
+        if not leftovers:
+            return texts, np.ascontiguousarray(vecs, dtype=np.float32)
+        left = {id(m) for m in leftovers}
+        fast_iter = iter(range(len(texts)))
+        out_t, out_v = [], []
+        for m in msgs:
+            if id(m) not in left:
+                i = next(fast_iter)
+                out_t.append(texts[i])
+                out_v.append(vecs[i])
+                continue
+            got = self._decode_all("queries_embed", [m])
+            if got and self._check_vec("queries_embed", m, got[0][1].get("embedding")):
+                out_t.append(got[0][1].get("query"))
+                out_v.append(np.asarray(got[0][1]["embedding"], dtype=np.float32))
+        dim = self.table.index.dim
+        return out_t, (np.ascontiguousarray(np.stack(out_v), dtype=np.float32) if out_v else np.empty((0, dim), np.float32))
 
     def _emit_results(self, texts, score, idx) -> None:
         header = self.codec.header("search_results")
         n_out = schemas.RESULTS_PER_QUERY
         for r, q in enumerate(texts):
-            self.producer.produce("search_results",
-                                  value=header + search_results_avro_body(self.table, q, score[r], idx[r], n_out))
+            self.producer.produce("search_results", value=header + search_results_avro_body(
+                self.table, q, score[r], idx[r], n_out, self.score_mode))
         self.stats["searches"] += len(texts)
+
+    # ---- native batch path -------------------------------------------------------------------------------------------
+    def _query_buffers(self):
+        if self._qbuf is None:
+            dim = self.table.index.dim
+            try:        # page-locked: the engine DMAs straight from the decode buffer
+                from ..engine import pinned_array
+                self._qbuf = [pinned_array((self.max_batch, dim), np.float32) for _ in range(2)]
+            except Exception:
+                self._qbuf = [np.empty((self.max_batch, dim), np.float32) for _ in range(2)]
+        return self._qbuf
+
+    def _decode_raw_batch(self, raw, slot):
+        """One partition slice -> (n_good, vectors view, text buffer, text_off, text_len).  Fast shape natively; anything
+        else through the generic codec (which also quarantines), in place, so the batch keeps its order."""
+        topic, part, first, n, data = raw
+        lib, dim = self._wire, self.table.index.dim
+        voff = np.empty(n, np.uint64)
+        vlen = np.empty(n, np.uint32)
+        rc = lib.sa_wire_split_log(data, len(data), n, voff.ctypes.data, vlen.ctypes.data, None, None, None)
+        if rc:
+            raise avro.AvroError("corrupt log slice: " + lib.sa_last_error().decode())
+        vecs = self._query_buffers()[slot]
+        toff = np.empty(n, np.uint64)
+        tlen = np.empty(n, np.uint32)
+        status = np.empty(n, np.uint8)
+        n_ok = C.c_int()
+        rc = lib.sa_wire_decode_queries_embed(data, voff.ctypes.data, vlen.ctypes.data, n, dim,
+                                              self.codec.schema_id("queries_embed"), vecs.ctypes.data, toff.ctypes.data,
+                                              tlen.ctypes.data, status.ctypes.data, C.byref(n_ok))
+        if rc:
+            raise avro.AvroError(lib.sa_last_error().decode())
+        text_buf = data
+        if n_ok.value != n:
+            extra = bytearray()
+            keep = np.ones(n, bool)
+            for i in np.flatnonzero(status).tolist():
+                value = None if vlen[i] == 0xFFFFFFFF else data[int(voff[i]):int(voff[i]) + int(vlen[i])]
+                m = Message(topic, part, first + i, None, value, 0)
+                got = self._decode_all("queries_embed", [m])
+                vec = got[0][1].get("embedding") if got else None
+                if not got or not self._check_vec("queries_embed", m, vec):
+                    keep[i] = False
+                    continue
+                vecs[i] = vec
+                q = got[0][1].get("query")
+                if q is None:
+                    tlen[i] = 0xFFFFFFFF
+                else:
+                    qb = q.encode("utf-8")
+                    toff[i] = len(data) + len(extra)
+                    tlen[i] = len(qb)
+                    extra += qb
+            if extra:
+                text_buf = data + bytes(extra)
+            if not keep.all():
+                good = np.flatnonzero(keep)
+                vecs[:len(good)] = vecs[good]
+                toff, tlen = toff[good], tlen[good]
+                n = len(good)
+        return n, vecs[:n], text_buf, toff, tlen
+
+    def _emit_results_native(self, n, text_buf, toff, tlen, score, idx) -> None:
+        lib, t = self._wire, self.table
+        rows = np.ascontiguousarray(idx, dtype=np.int64)
+        score = np.ascontiguousarray(score, dtype=np.float32)
+        k = score.shape[1]
+        rec_off = np.empty(n + 1, np.uint64)
+        need = C.c_uint64()
+        args = (n, k, schemas.RESULTS_PER_QUERY, self.codec.schema_id("search_results"), text_buf, toff.ctypes.data,
+                tlen.ctypes.data, score.ctypes.data, rows.ctypes.data, t.arena_document_id.data.ctypes.data,
+                t.arena_document_id.off.ctypes.data, t.arena_chunk.data.ctypes.data, t.arena_chunk.off.ctypes.data, len(t),
+                1 if self.score_mode == "atlas" else 0, int(time.time() * 1000))
+        lib.sa_wire_encode_search_results(*args, None, 0, rec_off.ctypes.data, C.byref(need))   # sizing pass
+        out = np.empty(int(need.value), np.uint8)
+        rc = lib.sa_wire_encode_search_results(*args, out.ctypes.data, out.size, rec_off.ctypes.data, C.byref(need))
+        if rc:
+            raise avro.AvroError(lib.sa_last_error().decode())
+        self.producer.produce_framed("search_results", out.data, rec_off[:n])
+        self.stats["searches"] += n
+
+    def _note_latency(self, t_submit, n):
+        self._lat_ms.append((time.perf_counter() - t_submit) * 1e3)
+        self.stats["search_batches"] += 1
+        if self._metrics_file and time.time() - self._metrics_t0 >= self._metrics_every_s:
+            self.write_metrics()
+
+    def write_metrics(self) -> dict:
+        """One JSON line of batch-latency percentiles (consume -> results flushed) and throughput since the last line."""
+        now = time.time()
+        lat = np.asarray(self._lat_ms or [0.0])
+        row = {"ts": now, "batches": len(self._lat_ms), "queries": self.stats["searches"] - self._metrics_q0,
+               "qps": (self.stats["searches"] - self._metrics_q0) / max(now - self._metrics_t0, 1e-9),
+               "batch_latency_ms": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
+                                    "max": float(lat.max())}, "table_rows": len(self.table)}
+        if self._metrics_file:
+            with open(self._metrics_file, "a") as f:
+                f.write(json.dumps(row) + "\n")
+        self._lat_ms, self._metrics_t0, self._metrics_q0 = [], now, self.stats["searches"]
+        return row
 
     def stage_search(self) -> int:
         """queries_embed -> VECTOR_SEARCH_AGG -> search_results.  When the index offers the split host call
         (``search_host_submit`` / ``search_host_wait``), batches are software-pipelined: batch i+1 is read and decoded
         while the GPU searches batch i.  Offsets of a batch are committed only after its results are flushed."""
+        if self._wire is not None and len(self.table) == self.table.arena_document_id.n:
+            return self._stage_search_native()
+        return self._stage_search_generic()
+
+    def _stage_search_native(self) -> int:
+        c = self.consumers["queries_embed"]
+        index = self.table.index
+        pipelined = hasattr(index, "search_host_submit")
+        total, slot, pending = 0, 0, None
+        while True:
+            raw = c.consume_raw(self.max_batch)
+            batch = None
+            if raw is not None:
+                total += raw[3]
+                t_in = time.perf_counter()
+                n, vecs, text_buf, toff, tlen = self._decode_raw_batch(raw, slot)
+                batch = (raw, n, vecs, text_buf, toff, tlen, t_in)
+                if n and pipelined:
+                    t0 = time.perf_counter()
+                    index.search_host_submit(vecs, self.k, slot)
+                    self.stats["search_seconds"] += time.perf_counter() - t0
+            if pending is not None:      # collect the previous batch while the new one runs
+                (p_raw, p_n, _, p_text, p_toff, p_tlen, p_t), p_slot = pending
+                t0 = time.perf_counter()
+                score, idx = index.search_host_wait(p_slot)
+                self.stats["search_seconds"] += time.perf_counter() - t0
+                self._emit_results_native(p_n, p_text, p_toff, p_tlen, score, idx)
+                c.commit_upto(p_raw[0], p_raw[1], p_raw[2] + p_raw[3])
+                self._note_latency(p_t, p_n)
+                pending = None
+            if batch is None:
+                break
+            raw, n, vecs, text_buf, toff, tlen, t_in = batch
+            if n and pipelined:
+                pending = (batch, slot)
+                slot ^= 1
+            else:
+                if n:
+                    t0 = time.perf_counter()
+                    score, idx = index.search_host(vecs, self.k)
+                    self.stats["search_seconds"] += time.perf_counter() - t0
+                    self._emit_results_native(n, text_buf, toff, tlen, score, idx)
+                    self._note_latency(t_in, n)
+                self.producer.flush()  # carries any quarantined records of this batch
+                c.commit_upto(raw[0], raw[1], raw[2] + raw[3])
+        return total
+
+    def _stage_search_generic(self) -> int:
         c = self.consumers["queries_embed"]
         index = self.table.index
         pipelined = hasattr(index, "search_host_submit")
@@ -263,19 +461,20 @@ class Lab2Pipeline:
                 index.search_host_submit(batch[2], self.k, slot)
                 self.stats["search_seconds"] += time.perf_counter() - t0
             if pending is not None:  # collect the previous batch while the new one runs
-                p_msgs, p_texts, p_slot = pending
+                p_msgs, p_texts, p_slot, p_t = pending
                 t0 = time.perf_counter()
                 score, idx = index.search_host_wait(p_slot)
                 self.stats["search_seconds"] += time.perf_counter() - t0
                 self._emit_results(p_texts, score, idx)
                 self.producer.flush()
                 c.commit_offsets(p_msgs)
+                self._note_latency(p_t, len(p_texts))
                 pending = None
             if batch is None:
                 break
             msgs, texts, vecs = batch
             if len(texts) and pipelined:
-                pending = (msgs, texts, slot)
+                pending = (msgs, texts, slot, time.perf_counter())
                 slot ^= 1
             else:
                 if len(texts):
@@ -283,6 +482,7 @@ class Lab2Pipeline:
                     score, idx = index.search_host(vecs, self.k)
                     self.stats["search_seconds"] += time.perf_counter() - t0
                     self._emit_results(texts, score, idx)
+                    self._note_latency(t0, len(texts))
                 self.producer.flush()  # also carries any quarantined records of this batch
                 c.commit_offsets(msgs)
         return total
@@ -321,7 +521,21 @@ class Lab2Pipeline:
                 break
         return total
 
-    def run_forever(self, idle_sleep: float = 0.05, stop=lambda: False) -> None:
+    def snapshot(self, directory: str) -> int:
+        """Checkpoint the table together with the `documents_embed` offsets its content reaches (everything the sink has
+        consumed is in the table by the time a stage returns).  Written atomically; see VectorTable.save."""
+        pos = self.consumers["documents_embed"].positions("documents_embed")
+        n = self.table.save(directory, {f"documents_embed-{p}": o for p, o in pos.items()})
+        self.stats["snapshots"] += 1
+        self._sink_dirty = False
+        return n
+
+    def run_forever(self, idle_sleep: float = 0.05, stop=lambda: False, snapshot_dir: str | None = None,
+                    snapshot_every_s: float = 30.0) -> None:
+        last = time.time()
         while not stop():
             if self.run_once() == 0:
                 time.sleep(idle_sleep)
+            if snapshot_dir and self._sink_dirty and time.time() - last >= snapshot_every_s:
+                self.snapshot(snapshot_dir)
+                last = time.time()

@@ -137,7 +137,12 @@ class ShardedIndex:
 class MultiGpuIndex:
     """All GPUs of a box driven by ONE process: shard g of the corpus on device g, one NCCL communicator created inside
     the C ABI (``sa_comm_create``), host queries in and merged host results out through ``sa_gather_merge``.  This is the
-    serving form (``sa_serve --gpus N``): no torchrun, no torch.distributed."""
+    serving form (``sa_serve --gpus N``): no torchrun, no torch.distributed.
+
+    It offers the interface ``operator.VectorTable`` expects of an index (``append`` -> first row, ``delete_rows``,
+    ``reset``, ``__len__``, ``search_host[_submit/_wait]``) with DENSE row ids in append order; inside, append batches go
+    round-robin to the shards ("append-only streams go round-robin by epoch") and the library's
+    global rows (shard * capacity + local row) are translated back through a per-shard table."""
 
     def __init__(self, dim: int, capacity_per_gpu: int, max_batch: int, max_k: int, n_gpus: int | None = None):
         from . import capi
@@ -146,7 +151,7 @@ class MultiGpuIndex:
         if n < 1 or n > torch.cuda.device_count():
             raise ValueError(f"n_gpus {n} outside [1, {torch.cuda.device_count()}]")
         self.n = n
-        self.dim, self.capacity_per_gpu = dim, capacity_per_gpu
+        self.dim, self.capacity_per_gpu = dim, int(capacity_per_gpu)
         self.shards = [VectorIndex(dim=dim, capacity=capacity_per_gpu, max_batch=max_batch, max_k=max_k, device=g)
                        for g in range(n)]
         self.lib = self.shards[0].lib
@@ -158,8 +163,11 @@ class MultiGpuIndex:
         capi.check(self.lib.sa_comm_create(C.byref(h), n, devs), "sa_comm_create")
         self._comm = h
         self._engines = (C.c_void_p * n)(*[s._h for s in self.shards])
+        self._offsets = (C.c_int64 * n)(*[g * self.capacity_per_gpu for g in range(n)])
         self._inflight = {}
-        self._next = 0   # round-robin appends keep the shards balanced
+        self._next = 0                                    # round-robin appends keep the shards balanced
+        self._dense_of = [np.zeros(0, np.int64) for _ in range(n)]   # per shard: local row -> dense row
+        self._where: list[tuple[int, int]] = []           # dense row -> (shard, local row)
 
     def close(self) -> None:
         if self._comm is not None:
@@ -169,38 +177,71 @@ class MultiGpuIndex:
             s.close()
 
     def __len__(self) -> int:
-        return sum(len(s) for s in self.shards)
+        return len(self._where)
 
-    # Global row id = shard * capacity_per_gpu + local row: append-only streams go round-robin by batch,
-    # so an id never changes when other shards grow.
-    def offsets(self):
-        return (C.c_int64 * self.n)(*[g * self.capacity_per_gpu for g in range(self.n)])
+    def reset(self) -> None:
+        for s in self.shards:
+            s.reset()
+        self._dense_of = [np.zeros(0, np.int64) for _ in range(self.n)]
+        self._where = []
+        self._next = 0
 
-    def locate(self, global_row: int) -> tuple[int, int]:
-        return divmod(int(global_row), self.capacity_per_gpu)
-
-    def append(self, rows_f32: np.ndarray) -> np.ndarray:
-        """Append a batch of fp32 embeddings to the next shard (round-robin).  Returns their global row ids."""
+    def append(self, rows_f32: np.ndarray) -> int:
+        """Append a batch of fp32 embeddings to the next shard (round-robin).  Returns the first (dense) row id."""
+        rows_f32 = np.ascontiguousarray(rows_f32, dtype=np.float32)
+        first = len(self._where)
+        if len(rows_f32) == 0:
+            return first
         g = self._next
         self._next = (self._next + 1) % self.n
-        first = self.shards[g].append(rows_f32)
-        return g * self.capacity_per_gpu + first + np.arange(len(rows_f32), dtype=np.int64)
+        lo = self.shards[g].append(rows_f32)
+        m = len(rows_f32)
+        self._dense_of[g] = np.concatenate([self._dense_of[g], np.arange(first, first + m, dtype=np.int64)])
+        self._where.extend((g, lo + j) for j in range(m))
+        return first
+
+    def delete_rows(self, rows) -> None:
+        by_shard: dict[int, list[int]] = {}
+        for r in rows:
+            g, l = self._where[int(r)]
+            by_shard.setdefault(g, []).append(l)
+        for g, ls in by_shard.items():
+            self.shards[g].delete_rows(ls)
+
+    def _to_dense(self, global_rows: np.ndarray) -> np.ndarray:
+        out = np.full(global_rows.shape, -1, dtype=np.int64)
+        ok = global_rows >= 0
+        g = global_rows[ok] // self.capacity_per_gpu
+        l = global_rows[ok] % self.capacity_per_gpu
+        dense = np.empty(len(g), dtype=np.int64)
+        for s in range(self.n):
+            m = g == s
+            if m.any():
+                dense[m] = self._dense_of[s][l[m]]
+        out[ok] = dense
+        return out
 
     def search_host_submit(self, q_f32: np.ndarray, k: int, slot: int = 0) -> None:
         from . import capi
         q = np.ascontiguousarray(q_f32, dtype=np.float32)
         self._inflight[slot] = (q, q.shape[0], k)
         capi.check(self.lib.sa_gather_merge_submit(self._comm, self._engines, slot, q.ctypes.data, q.shape[0], k,
-                                                   self.offsets()), "sa_gather_merge_submit")
+                                                   self._offsets), "sa_gather_merge_submit")
 
     def search_host_wait(self, slot: int = 0, out=None):
+        """(score f32 [nq, k], dense row i64 [nq, k]); ties between shards resolve by the library's global row order
+        (shard, then local row), not by dense id."""
         from . import capi
         _, nq, k = self._inflight.pop(slot)
-        if out is None:
-            out = (np.empty((nq, k), np.float32), np.empty((nq, k), np.int64))
-        capi.check(self.lib.sa_gather_merge_wait(self._comm, self._engines, slot, out[0].ctypes.data,
-                                                 out[1].ctypes.data), "sa_gather_merge_wait")
-        return out
+        score = np.empty((nq, k), np.float32) if out is None else out[0]
+        rows = np.empty((nq, k), np.int64)
+        capi.check(self.lib.sa_gather_merge_wait(self._comm, self._engines, slot, score.ctypes.data, rows.ctypes.data),
+                   "sa_gather_merge_wait")
+        dense = self._to_dense(rows)
+        if out is not None:
+            out[1][:] = dense
+            return out
+        return score, dense
 
     def search_host(self, q_f32: np.ndarray, k: int, out=None):
         self.search_host_submit(q_f32, k, 0)

@@ -3,6 +3,7 @@ this path (testing/e2e/test_lab2.py:74-135): `queries` has >= 1 message -> `sear
 `search_results_response[0].response` is non-empty.  On a CPU box the vector index is an oracle-backed double
 (tests/doubles.py); `test_pipeline_on_gpu` runs the same flow through the CUDA engine."""
 import json
+import struct
 
 import numpy as np
 import pytest
@@ -387,7 +388,9 @@ def test_sa_serve_cli_snapshot_resume_with_a_double(tmp_path, capsys, monkeypatc
     assert sa_serve.main(["--log-dir", logd, "--once", "--snapshot-dir", snap]) == 0
     first = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
     assert first["documents"] == 21 and first["searches"] == 1
-    assert (tmp_path / "ckpt" / "columns.jsonl").exists() and (tmp_path / "ckpt" / "index.npz").exists()
+    man = json.load(open(tmp_path / "ckpt" / "manifest.json"))
+    assert man["rows"] == 21 and man["source_offsets"] == {"documents_embed-0": 21}
+    assert all((tmp_path / "ckpt" / f).exists() for f in man["files"].values())
     # second process: nothing new on `documents`, one new query; the table comes from the checkpoint
     assert lab2_publish_queries.main(["How do session windows work?", "--log-dir", logd]) == 0
     capsys.readouterr()
@@ -400,6 +403,124 @@ def test_sa_serve_cli_snapshot_resume_with_a_double(tmp_path, capsys, monkeypatc
     rows = [Codec(logd).decode(m.value()) for m in c.consume(10, 0.0)]
     assert [r["query"] for r in rows] == ["What about watermarks?", "How do session windows work?"]
     assert all(r["document_id_1"] for r in rows)
+    # third process: one more document arrived after the checkpoint -> the sink resumes at the checkpoint's offsets
+    (docs / "late.md").write_text("---\ntitle: Late\n---\nSession windows group events by gaps of inactivity.")
+    assert publish_docs.main(["--docs-dir", str(docs), "--log-dir", logd]) == 0        # republish: 22 records, 21 upserts
+    capsys.readouterr()
+    assert sa_serve.main(["--log-dir", logd, "--once", "--snapshot-dir", snap]) == 0
+    third = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert third["documents"] == 22
+    man2 = json.load(open(tmp_path / "ckpt" / "manifest.json"))
+    assert man2["generation"] == man["generation"] + 2 and man2["source_offsets"] == {"documents_embed-0": 43}
+    assert not (tmp_path / "ckpt" / man["files"]["columns"]).exists()      # old generations are removed
+
+
+def test_restart_without_a_checkpoint_rebuilds_the_table_from_the_log(tmp_path, capsys, monkeypatch):
+    """the table is volatile (HBM), the log is durable.  A restarted sa_serve without --snapshot-dir
+    must rebuild the table from `documents_embed` instead of trusting the sink's committed offsets -- the README
+    quick-start runs `sa_serve --once` repeatedly, and the second run used to answer with null documents."""
+    import qsa_b200.engine as engine_mod
+    from scripts import sa_serve
+
+    class Index(OracleIndex):
+        def __init__(self, dim=1536, capacity=0, max_batch=0, max_k=0, device=None):
+            super().__init__(dim, capacity)
+
+    monkeypatch.setattr(engine_mod, "VectorIndex", Index)
+    docs, logd = tmp_path / "docs", str(tmp_path / "topics")
+    write_docs(docs, 12)
+    assert publish_docs.main(["--docs-dir", str(docs), "--log-dir", logd]) == 0
+    assert lab2_publish_queries.main(["What about watermarks?", "--log-dir", logd]) == 0
+    assert sa_serve.main(["--log-dir", logd, "--once"]) == 0
+    assert lab2_publish_queries.main(["How do tumble windows work?", "--log-dir", logd]) == 0
+    capsys.readouterr()
+    assert sa_serve.main(["--log-dir", logd, "--once"]) == 0                       # a NEW process: empty table at start
+    second = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert second["documents"] == 13 and second["searches"] == 1                   # table rebuilt, `documents` NOT re-embedded
+    c = Consumer({"log.dir": logd, "group.id": "t"}); c.subscribe(["search_results"])
+    rows = [Codec(logd).decode(m.value()) for m in c.consume(10, 0.0)]
+    assert [r["query"] for r in rows] == ["What about watermarks?", "How do tumble windows work?"]
+    assert all(r["document_id_1"] is not None and r["chunk_1"] for r in rows)
+    c = Consumer({"log.dir": logd, "group.id": "t2"}); c.subscribe(["documents_embed"])
+    assert len(c.consume(100, 0.0)) == 13                                          # nothing was produced twice
+
+
+def _odd_queries_embed_records(codec, dim, g):
+    """queries_embed records in every shape the wire allows: the usual one, a null query, a multi-block array, a
+    null item, a wrong length, a non-finite value, garbage."""
+    from qsa_b200.wire import avro
+    sid_hdr = codec.header("queries_embed")
+    vec = lambda: g.standard_normal(dim).astype(np.float32)
+    usual = [codec.encode("queries_embed", {"query": f"q{i} é", "embedding": vec()}) for i in range(5)]
+    null_q = codec.encode("queries_embed", {"query": None, "embedding": vec()})
+    v = vec()
+    body = bytearray(b"\x02"); avro.write_long(body, 2); body += b"mb"; body += b"\x02"
+    half = dim // 2
+    for part in (v[:half], v[half:]):                      # two blocks, the second one in the negative-count form
+        blk = b"".join(b"\x02" + struct.pack("<f", float(x)) for x in part)
+        if part is v:
+            avro.write_long(body, len(part))
+        else:
+            avro.write_long(body, -len(part)); avro.write_long(body, len(blk))
+        body += blk
+    body += b"\x00"
+    multi = sid_hdr + bytes(body)
+    null_item = codec.encode("queries_embed", {"query": "ni", "embedding": [1.0, None] + [0.5] * (dim - 2)})
+    wrong_len = codec.encode("queries_embed", {"query": "wl", "embedding": vec()[: dim - 3]})
+    nonfinite = codec.encode("queries_embed", {"query": "nf", "embedding": np.r_[vec()[:-1], np.float32("inf")]})
+    return usual[:2] + [null_q, multi] + usual[2:4] + [null_item, wrong_len, b"\x07garbage", nonfinite, b""] + usual[4:]
+
+
+@pytest.mark.parametrize("score_mode", ["cosine", "atlas"])
+def test_native_search_stage_equals_the_generic_codec_byte_for_byte(tmp_path, score_mode):
+    """The native batch path (sa_wire_*: split, decode, encode + framing) and the generic Python codec path must put the
+    SAME bytes on `search_results` and quarantine the SAME records, for usual and unusual record shapes alike."""
+    import struct as _s
+    globals()["struct"] = _s
+    g = np.random.default_rng(11)
+    dim = 64
+    outs, dlqs = {}, {}
+    for name in ("generic", "native"):
+        logd = str(tmp_path / name)
+        idx = PipelinedOracleIndex(dim)
+        table = VectorTable(idx)
+        gg = np.random.default_rng(12)
+        table.upsert_many([f"d{i}" if i % 7 else None for i in range(50)], [f"chunk {i} ü" if i % 5 else None for i in range(50)],
+                          gg.standard_normal((50, dim)).astype(np.float32))
+        pipe = Lab2Pipeline(logd, table, k=5, max_batch=7, native=(name == "native"), score_mode=score_mode)
+        assert (pipe._wire is not None) == (name == "native")
+        p = Producer({"log.dir": logd})
+        for raw in _odd_queries_embed_records(pipe.codec, dim, np.random.default_rng(13)):
+            p.produce("queries_embed", value=raw)
+        p.produce("queries_embed", value=None)
+        p.flush()
+        assert pipe.stage_search() == 13 and pipe.stage_search() == 0
+        pipe.producer.flush()
+        c = Consumer({"log.dir": logd, "group.id": "t"}); c.subscribe(["search_results"])
+        outs[name] = [m.value() for m in c.consume(100, 0.0)]
+        c = Consumer({"log.dir": logd, "group.id": "t"}); c.subscribe(["queries_embed.dlq"])
+        dlqs[name] = [(m.key(), m.value()) for m in c.consume(100, 0.0)]
+        assert pipe.stats["quarantined"] == len(dlqs[name]) == 6 and pipe.stats["searches"] == 7
+    assert outs["native"] == outs["generic"] and len(outs["native"]) == 7
+    assert dlqs["native"] == dlqs["generic"]
+    rec = Codec(str(tmp_path / "native")).decode(outs["native"][2])
+    assert rec["query"] is None and (0 <= rec["score_1"] <= 1 if score_mode == "atlas" else True)
+
+
+def test_serve_metrics_file_has_latency_percentiles(tmp_path):
+    g = np.random.default_rng(2)
+    logd, mf = str(tmp_path / "topics"), str(tmp_path / "metrics.jsonl")
+    idx = PipelinedOracleIndex(32)
+    table = VectorTable(idx)
+    table.upsert_many([f"d{i}" for i in range(20)], [f"c{i}" for i in range(20)], g.standard_normal((20, 32)).astype(np.float32))
+    pipe = Lab2Pipeline(logd, table, k=3, max_batch=8, metrics_file=mf, metrics_every_s=0.0)
+    p = Producer({"log.dir": logd})
+    for i in range(30):
+        p.produce("queries_embed", value=pipe.codec.encode("queries_embed", {"query": f"q{i}", "embedding": g.standard_normal(32).astype(np.float32)}))
+    p.flush()
+    assert pipe.stage_search() == 30
+    rows = [json.loads(l) for l in open(mf)]
+    assert sum(r["queries"] for r in rows) == 30 and all(r["batch_latency_ms"]["p99"] >= r["batch_latency_ms"]["p50"] >= 0 for r in rows)
 
 
 def test_config1_two_thousand_docs_plumbing_on_cpu(tmp_path):
