@@ -80,6 +80,7 @@ def parse_args():
     ap.add_argument("--workers", type=int, default=0, help="data-generation / oracle worker processes (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip cpu_baseline / recall (profiling runs)")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra BASELINE configs")
+    ap.add_argument("--no-pipeline", action="store_true", help="skip the Avro-in / Avro-out serve-stage measurement")
     ap.add_argument("--extra", default="cfg2,cfg4,cfg5", help="which extra configs to run")
     ap.add_argument("--data", default="numpy", choices=["numpy", "philox"],
                     help="philox: device generator for chunks >= 1 (quick profiling runs only; chunk 0 stays canonical)")
@@ -654,6 +655,106 @@ class Workload:
         return r
 
 
+def pipeline_e2e(env, index_like, n_total, dim, B, k, q_bits, est_batch_s, min_timed_s, check_rows=None):
+    """QPS_e2e as SURVEY.md section 8d defines it: Confluent-framed Avro `queries_embed` records on the file-log transport
+    in, `search_results` records out -- read, decode, H2D, search, D2H, encode, append, commit -- through the product's own
+    serve stage (pipeline/serve.py::Lab2Pipeline.stage_search, native batch codecs of include/sa_wire.h).  Every rank
+    reads its own copy of the same topic, so the sharded search's collectives pair up; all ranks end with the same output.
+    The table's non-vector columns are synthetic fixed-width strings ("doc-<row>" / a 96-byte chunk naming the row)."""
+    import ctypes as C
+    import shutil
+    import tempfile
+    from qsa_b200 import capi
+    from qsa_b200.operator import VectorTable
+    from qsa_b200.pipeline.serve import Codec, Lab2Pipeline
+    from qsa_b200.transport.filelog import Consumer
+    torch, rank, world = env["torch"], env["rank"], env["world"]
+    lib = capi.load()
+    logd = tempfile.mkdtemp(prefix=f"sa_bench_topics_r{rank}_")
+    try:
+        # ---- side table: rows -> pre-serialised Avro ["null","string"] values, built without a Python loop
+        table = VectorTable(index_like)
+        digits = ((np.arange(n_total, dtype=np.int64)[:, None] // 10 ** np.arange(8, -1, -1)) % 10 + 48).astype(np.uint8)
+
+        def fixed(prefix: bytes, pad: bytes):
+            body_len = len(prefix) + 9 + len(pad)
+            assert body_len < 64                     # one-byte Avro length
+            m = np.empty((n_total, 2 + body_len), np.uint8)
+            m[:, 0], m[:, 1] = 2, body_len << 1
+            m[:, 2:2 + len(prefix)] = np.frombuffer(prefix, np.uint8)
+            m[:, 2 + len(prefix):2 + len(prefix) + 9] = digits
+            if pad:
+                m[:, 2 + len(prefix) + 9:] = np.frombuffer(pad, np.uint8)
+            return m.reshape(-1), np.arange(n_total + 1, dtype=np.uint64) * np.uint64(2 + body_len)
+        for arena, (data, off) in ((table.arena_document_id, fixed(b"doc-", b"")),
+                                   (table.arena_chunk, fixed(b"chunk of row ", b" lorem ipsum dolor sit amet, consectetur."))):
+            arena.data, arena.off, arena.n, arena.used = data, off, n_total, len(data)
+        table.document_id = range(n_total)           # len(table) == n_total; the native stage reads the arenas only
+        pipe = Lab2Pipeline(logd, table, k=k, max_batch=B, native=True, group=f"bench-r{rank}")
+        # ---- the input topic: n_batches x B records, encoded and framed natively, one append per batch
+        n_batches = max(4, int(math.ceil(min_timed_s / max(est_batch_s, 1e-6))))
+        n_batches = min(n_batches, 256)
+        from oracle import bruteforce as bf
+        vec = np.ascontiguousarray(bf.bf16_bits_to_f32(q_bits))
+        texts = [f"question {i}".encode() for i in range(B)]
+        tbuf = b"".join(texts)
+        tlen = np.array([len(t) for t in texts], np.uint32)
+        toff = np.concatenate([[0], np.cumsum(tlen[:-1], dtype=np.uint64)]).astype(np.uint64)
+        rec_off = np.empty(B + 1, np.uint64)
+        need = C.c_uint64()
+        sid = pipe.codec.schema_id("queries_embed")
+        lib.sa_wire_encode_queries_embed(B, dim, sid, tbuf, toff.ctypes.data, tlen.ctypes.data, vec.ctypes.data, 0, None, 0,
+                                         rec_off.ctypes.data, C.byref(need))
+        out = np.empty(int(need.value), np.uint8)
+        capi.check(lib.sa_wire_encode_queries_embed(B, dim, sid, tbuf, toff.ctypes.data, tlen.ctypes.data, vec.ctypes.data,
+                                                    int(time.time() * 1000), out.ctypes.data, out.size, rec_off.ctypes.data,
+                                                    C.byref(need)), "sa_wire_encode_queries_embed")
+        for _ in range(n_batches + 2):
+            pipe.producer.produce_framed("queries_embed", out.data, rec_off[:B])
+        # ---- warm-up on two batches (also page-locks the staging buffers), then the timed drain
+        pipe.max_batch = B
+        c = pipe.consumers["queries_embed"]
+        real_consume = c.consume_raw
+        budget = [2]
+
+        def limited(nmax):
+            if budget[0] <= 0:
+                return None
+            budget[0] -= 1
+            return real_consume(nmax)
+        c.consume_raw = limited
+        assert pipe.stage_search() == 2 * B
+        c.consume_raw = real_consume
+        env["barrier"]()
+        t0 = time.perf_counter()
+        moved = pipe.stage_search()
+        torch.cuda.synchronize()
+        env["barrier"]()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            dt = env["allmax"]([dt])[0]
+        assert moved == n_batches * B, (moved, n_batches, B)
+        res = {"value": moved / dt, "unit": UNIT, "records": moved, "batches": n_batches, "timed_region_s": dt,
+               "bytes_in_per_record": int(rec_off[1]), "api": "Lab2Pipeline.stage_search over the file-log transport: "
+               "consume_raw -> sa_wire_split_log / sa_wire_decode_queries_embed -> " +
+               ("sa_search_host_submit/_wait" if world == 1 else "sa_sharded_search_host_submit/_wait") +
+               " -> sa_wire_encode_search_results -> produce_framed -> commit",
+               "batch_latency_ms": pipe.write_metrics()["batch_latency_ms"]}
+        if rank == 0:
+            cs = Consumer({"log.dir": logd, "group.id": "check"})
+            cs.subscribe(["search_results"])
+            msgs = cs.consume(B, 0.0)
+            recs = [Codec(logd).decode(m.value()) for m in msgs[:64]]
+            res["bytes_out_per_record"] = len(msgs[0].value())
+            ok = all(r["query"] == f"question {i}" for i, r in enumerate(recs))
+            if check_rows is not None:     # the same queries went through the device-resident loop: same rows expected
+                ok = ok and all(r[f"document_id_{j + 1}"] == "doc-%09d" % check_rows[i][j] for i, r in enumerate(recs) for j in range(3))
+            res["output_matches_device_path"] = bool(ok)
+        return res
+    finally:
+        shutil.rmtree(logd, ignore_errors=True)
+
+
 def upload(host, ix, torch, seed, dim, lo_row, hi_row, n_total, data_mode):
     """Generate rows [lo_row, hi_row) of corpus `seed` on the host pool and copy each piece to the device as it
     completes; commit.  data_mode == 'philox': only chunk 0 is canonical, the rest comes from the device generator."""
@@ -807,6 +908,18 @@ def run_b200(a):
             "clocks": m["clocks"], "clocks_whole_region": m["clocks_whole_region"], "roofline": m["roofline"],
         }
 
+    # ---- QPS_e2e through the serve stage (Avro in, Avro out, file-log transport), same queries, same engine
+    if not a.no_pipeline:
+        try:
+            rows_dev = out[1].cpu().numpy()
+            pe = pipeline_e2e(env, ix if world == 1 else sh, n_total, dim, B, k, q_bits, m["ms_per_batch"] * 1e-3,
+                              a.min_timed_s, check_rows=rows_dev)
+            if rank == 0:
+                result["e2e_pipeline"] = pe
+        except Exception as exc:
+            if world > 1:
+                raise
+            result["e2e_pipeline"] = {"error": f"{type(exc).__name__}: {exc}"}
     # ---- outside the timed region: recall vs numpy, cuBLAS on the same box, CPU baseline
     if not a.no_cpu:
         try:

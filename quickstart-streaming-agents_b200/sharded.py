@@ -71,6 +71,10 @@ class ShardedIndex:
             self.index.lib.sa_comm_destroy(self._comm)
             self._comm = None
 
+    @property
+    def dim(self) -> int:
+        return self.index.dim
+
     # ------------------------------------------------------------------ device-resident queries
     def search(self, q: torch.Tensor, k: int):
         """q: [nq, dim] bf16 on this rank's device (identical on every rank).  Returns (score f32 [nq,k],
