@@ -855,9 +855,11 @@ def run_b200(a):
             q = bf.synth_queries(seed, nq, d, chunk0_bits)
         if world == 1:
             return q
-        t = torch.from_numpy(q.view(np.int16)).cuda() if rank == 0 else torch.empty((nq, d), dtype=torch.int16, device="cuda")
+        # NCCL has no 16-bit integer type: ship the bit patterns as bytes
+        t = (torch.from_numpy(q.view(np.uint8)).cuda() if rank == 0
+             else torch.empty((nq, 2 * d), dtype=torch.uint8, device="cuda"))
         dist.broadcast(t, src=0)
-        return t.cpu().numpy().view(np.uint16)
+        return np.ascontiguousarray(t.cpu().numpy()).view(np.uint16)
 
     maxB = max([B] + ([4096] if "cfg4" in extras else []))
     ix = VectorIndex(dim=dim, capacity=n_local, max_batch=maxB, max_k=k, device=local)

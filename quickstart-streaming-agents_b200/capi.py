@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsa_b200.so")
+LIB_PATH = os.environ.get("SA_LIB_PATH") or os.path.join(_HERE, "libsa_b200.so")   # SA_LIB_PATH: A/B experiment builds
 
 SA_OK = 0
 SA_ERR_CUDA = -1

@@ -192,52 +192,81 @@ struct TopList {
   }
 };
 
-// The per-value rule of the epilogue for one group of four consecutive rows whose maximum `m` already exceeds the
-// threshold: insert in (score desc, row asc) order while anything qualifies; account what does not in `drop`.
-template <int kKL>
-__host__ __device__ __forceinline__ void group_insert(TopList<kKL>& L, float s0, float s1, float s2, float s3, float m,
-                                                      int row) {
-  while (m > L.thr) {  // rare after warm-up: ~kKL/n per value
-    const int j = (s0 == m) ? 0 : (s1 == m) ? 1 : (s2 == m) ? 2 : 3;  // lowest row among equals first
-    const float sj = (j == 0) ? s0 : (j == 1) ? s1 : (j == 2) ? s2 : s3;  // == m, but keeps the element's own sign of zero
-    L.drop = max_nn(L.drop, L.sc[kKL - 1]);                           // the evicted tail (-inf while the list fills)
-    list_insert<kKL>(L.sc, L.id, sj, row + j);
-    L.thr = max_nn(L.sc[kKL - 1], L.thr_floor);
-    s0 = (j == 0) ? -INFINITY : s0;
-    s1 = (j == 1) ? -INFINITY : s1;
-    s2 = (j == 2) ? -INFINITY : s2;
-    s3 = (j == 3) ? -INFINITY : s3;
-    m = max_nn(max_nn(s0, s1), max_nn(s2, s3));
-  }
-  L.drop = max_nn(L.drop, m);  // whatever is left of the group was rejected (NaN = masked rows: ignored)
-}
-
 // One 32-column chunk: scale, reduce to the chunk maximum with full instruction-level parallelism, and only when that
-// beats the threshold (probability ~ 32 kKL / n after n rows) walk the groups.  Returns true if the slow path ran.
+// beats the threshold (probability ~ 32 kKL / n after n rows) take the insertion path.  Returns true if it ran.
+//
+// Insertion path: extract-max rounds over the whole chunk -- each round takes the thread's largest remaining value (the
+// lowest row among equals), inserts it, masks it and re-reduces -- until nothing beats the threshold.  A warp executes
+// as many rounds as its busiest lane needs (usually one or two), however the qualifying values are spread over the 32
+// rows; walking the rows group by group instead costs a round per group that ANY lane has a hit in, which during the
+// warm-up of a short scan (1M rows: 26 tiles per lane) was most of the epilogue's time.
 template <int kKL>
 __host__ __device__ __forceinline__ bool chunk_process(TopList<kKL>& L, float (&v)[kChunk], const float (&w)[kChunk],
                                                        int row_base) {
-  float g[8];
+  auto reduce = [&]() {
+    float g[8];
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-  for (int i = 0; i < 8; ++i) {
-    v[4 * i + 0] *= w[4 * i + 0];
-    v[4 * i + 1] *= w[4 * i + 1];
-    v[4 * i + 2] *= w[4 * i + 2];
-    v[4 * i + 3] *= w[4 * i + 3];
-    g[i] = max_nn(max_nn(v[4 * i + 0], v[4 * i + 1]), max_nn(v[4 * i + 2], v[4 * i + 3]));
-  }
-  const float m = max_nn(max_nn(max_nn(g[0], g[1]), max_nn(g[2], g[3])), max_nn(max_nn(g[4], g[5]), max_nn(g[6], g[7])));
+    for (int i = 0; i < 8; ++i)
+      g[i] = max_nn(max_nn(v[4 * i + 0], v[4 * i + 1]), max_nn(v[4 * i + 2], v[4 * i + 3]));
+    return max_nn(max_nn(max_nn(g[0], g[1]), max_nn(g[2], g[3])), max_nn(max_nn(g[4], g[5]), max_nn(g[6], g[7])));
+  };
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int i = 0; i < kChunk; ++i) v[i] *= w[i];
+  float m = reduce();
   if (!(m > L.thr)) {
     L.drop = max_nn(L.drop, m);
     return false;
   }
+#ifdef SA_EPI_GROUPWISE  // A/B build of the round-1 style walk, group of four rows by group (tools/gpu_ab.sh)
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-  for (int i = 0; i < 8; ++i)
-    group_insert<kKL>(L, v[4 * i + 0], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3], g[i], row_base + 4 * i);
+  for (int i = 0; i < 8; ++i) {
+    float s0 = v[4 * i], s1 = v[4 * i + 1], s2 = v[4 * i + 2], s3 = v[4 * i + 3];
+    float mg = max_nn(max_nn(s0, s1), max_nn(s2, s3));
+    while (mg > L.thr) {
+      const int j = (s0 == mg) ? 0 : (s1 == mg) ? 1 : (s2 == mg) ? 2 : 3;
+      const float sj = (j == 0) ? s0 : (j == 1) ? s1 : (j == 2) ? s2 : s3;
+      L.drop = max_nn(L.drop, L.sc[kKL - 1]);
+      list_insert<kKL>(L.sc, L.id, sj, row_base + 4 * i + j);
+      L.thr = max_nn(L.sc[kKL - 1], L.thr_floor);
+      s0 = (j == 0) ? -INFINITY : s0;
+      s1 = (j == 1) ? -INFINITY : s1;
+      s2 = (j == 2) ? -INFINITY : s2;
+      s3 = (j == 3) ? -INFINITY : s3;
+      mg = max_nn(max_nn(s0, s1), max_nn(s2, s3));
+    }
+    L.drop = max_nn(L.drop, mg);
+  }
+  return true;
+#endif
+  do {
+    int pos = kChunk - 1;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int j = kChunk - 2; j >= 0; --j) pos = (v[j] == m) ? j : pos;  // lowest row among equals first
+    float sj = m;
+    if (m == 0.f) {  // keep the element's own sign of zero (max(+0, -0) is +0)
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+      for (int j = 0; j < kChunk; ++j) sj = (j == pos) ? v[j] : sj;
+    }
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int j = 0; j < kChunk; ++j) v[j] = (j == pos) ? -INFINITY : v[j];
+    L.drop = max_nn(L.drop, L.sc[kKL - 1]);  // the evicted tail (-inf while the list fills)
+    list_insert<kKL>(L.sc, L.id, sj, row_base + pos);
+    L.thr = max_nn(L.sc[kKL - 1], L.thr_floor);
+    m = reduce();
+  } while (m > L.thr);
+  L.drop = max_nn(L.drop, m);  // whatever is left of the chunk was rejected (NaN = masked rows: ignored)
   return true;
 }
 
