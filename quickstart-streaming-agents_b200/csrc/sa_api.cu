@@ -99,7 +99,7 @@ struct DeviceGuard {
   if (_dg.rc != cudaSuccess) return fail(SA_ERR_CUDA, "cudaSetDevice(%d) failed: %s", (dev), cudaGetErrorString(_dg.rc))
 
 constexpr int kMaxLaunches = 16;
-constexpr int kDefaultL2Prefetch = 0;  // set from the sweep in tools/gpu_sweep.py (profiles/)
+constexpr int kDefaultPresample = 0;   // set from tools/gpu_worstcase.py / gpu_sweep.py (profiles/)
 constexpr int kTimingRing = 16;
 constexpr int kHostSlots = SA_HOST_SLOTS;
 
@@ -173,7 +173,7 @@ struct sa_engine {
   int opt_pace_max = -1;   // -1 = auto (8 x gain)
   int opt_unit_map = 0;
   int opt_list_len = 0;    // 0 = auto (16 when k <= 12, else 32)
-  int opt_l2_prefetch = -1; // K slices the scan's L2 prefetch stream runs ahead (-1 = auto, 0 = off)
+  int opt_presample = -1;  // tile stride of the sampling pre-pass that seeds the shared thresholds (-1 = auto, 0 = off)
   int opt_force_fix = 0;   // test hook: every (query, lane) goes through the exact fallback scan
   int64_t last_fix_entries = -1;  // option "count_fix": work-queue length of the last search (costs a host sync)
   int opt_count_fix = 0;
@@ -382,7 +382,7 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
     sp.part_idx = e->part_idx;
     sp.part_drop = e->part_drop;
     sp.corpus_evict_first = (lp.nqb == 1) ? 1 : 0;  // a tile nobody else will ask for: stream it through L2
-    sp.l2_prefetch = e->opt_l2_prefetch >= 0 ? e->opt_l2_prefetch : kDefaultL2Prefetch;
+    sp.tile_stride = 1;
     sp.lane_progress = nullptr;
     sp.max_drift = e->opt_max_drift >= 0 ? e->opt_max_drift : 1;
     sp.pace_gain = 0;
@@ -395,7 +395,10 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
       sp.lane_progress = e->lane_progress + li * e->num_sms;  // this launch's slice (zero: see sa_engine)
       sp.pace_gain = gain;
     }
-    sp.thr_shared = (e->opt_share_thresholds && lp.tl > 1) ? e->thr_shared + lp.q0 : nullptr;
+    const int presample = e->opt_presample >= 0 ? e->opt_presample : kDefaultPresample;
+    // a pre-pass only pays when every lane still has a long walk ahead of it after the sample
+    const bool do_presample = presample > 1 && e->opt_share_thresholds && num_tiles >= 4 * presample * lp.tl;
+    sp.thr_shared = (e->opt_share_thresholds && (lp.tl > 1 || do_presample)) ? e->thr_shared + lp.q0 : nullptr;
     sp.dbg_dots = nullptr;
     sp.dbg_tile = -1;
     sp.dbg_times = e->opt_record_times ? e->dbg_times : nullptr;
@@ -405,6 +408,39 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
     min_tl = std::min(min_tl, lp.tl);
 
     SA_CUDA(cudaEventRecord(tm.ev_scan[li][0], st));
+    if (do_presample) {
+      // Sampling pre-pass: the same kernel over every presample-th tile, then each query's kKL-th best of the sample
+      // becomes its shared threshold (a valid lower bound on its global kKL-th best).  The full scan then starts with
+      // thresholds near their final values whatever the order of the rows: an adversarial (e.g. ascending) order can no
+      // longer make every row an insertion (tools/gpu_worstcase.py).
+      sa::ScanParams pp = sp;
+      pp.tile_stride = presample;
+      pp.lane_progress = nullptr;  // no pacing: the pre-pass is short
+      pp.pace_gain = 0;
+      pp.prof = e->prof;
+      rc = launch_scan_dispatch(lp.cg, kl, sa::kModeProd, tq, e->tmap_c[lp.cg - 1], pp, grid, st);
+      if (rc) return rc;
+      sa::MergeParams bp = {};
+      bp.part_score = e->part_score;
+      bp.part_idx = e->part_idx;
+      bp.part_drop = e->part_drop;
+      bp.corpus = e->corpus;
+      bp.queries = qptr;
+      bp.dim = e->dim;
+      bp.nq = lp.nq;
+      bp.k = k;
+      bp.cg = lp.cg;
+      bp.nqb = lp.nqb;
+      bp.tl_count = lp.tl;
+      bp.unit_map = e->opt_unit_map;
+      bp.bound_out = e->thr_shared + lp.q0;
+      if (kl == 16)
+        sa::sa_merge_rescore_kernel<16><<<lp.nq, sa::kMergeThreads, 0, st>>>(bp);
+      else
+        sa::sa_merge_rescore_kernel<32><<<lp.nq, sa::kMergeThreads, 0, st>>>(bp);
+      SA_CUDA(cudaGetLastError());
+      tm.kernels += 2;
+    }
     rc = launch_scan_dispatch(lp.cg, kl, mode, tq, e->tmap_c[lp.cg - 1], sp, grid, st);
     if (rc) return rc;
     SA_CUDA(cudaEventRecord(tm.ev_scan[li][1], st));
@@ -1292,9 +1328,9 @@ int sa_set_option(sa_engine* e, const char* name, int64_t value) {
     e->opt_max_launch_qblocks = static_cast<int>(value);
     return SA_OK;
   }
-  if (!strcmp(name, "l2_prefetch")) {
-    if (value < -1 || value > 256) return fail(SA_ERR_ARG, "l2_prefetch must be in [-1, 256]");
-    e->opt_l2_prefetch = static_cast<int>(value);
+  if (!strcmp(name, "presample")) {
+    if (value < -1 || value > 4096) return fail(SA_ERR_ARG, "presample must be in [-1, 4096]");
+    e->opt_presample = static_cast<int>(value);
     return SA_OK;
   }
   if (!strcmp(name, "force_fix")) {
@@ -1399,6 +1435,7 @@ int sa_debug_tile_dots(sa_engine* e, const void* q_bf16_dev, int nq, int tile, i
   sp.part_idx = e->part_idx;
   sp.part_drop = e->part_drop;
   sp.corpus_evict_first = 0;
+  sp.tile_stride = 1;
   sp.lane_progress = nullptr;
   sp.max_drift = 0;
   sp.pace_gain = 0;

@@ -148,6 +148,8 @@ struct MergeParams {
   int* fix_count;           // zero at the start of a search
   FixQuery* fix_query;      // [search nq]
   int force_fix;            // test hook: 1 = treat every lane as ambiguous (the fallback then recomputes everything)
+  unsigned* bound_out;      // sampling pre-pass only (else nullptr): publish each query's kKL-th best score of the sample
+                            // into the scan's shared thresholds [nq] and do nothing else
 };
 
 constexpr int kMergeThreads = 160;  // >= kMaxLanes: one thread per tile lane in the head tournament
@@ -252,7 +254,8 @@ __global__ void __launch_bounds__(kMergeThreads) sa_merge_rescore_kernel(const M
   // ---- A_k: k rounds of arg-max over the heads of the (sorted) lane lists; thread t owns lane t
   int head = 0;
   unsigned long long kth = 0;  // key of the k-th best candidate, 0 if fewer than k exist
-  for (int round = 0; round < p.k; ++round) {
+  const int rounds = p.bound_out != nullptr ? kKL : p.k;
+  for (int round = 0; round < rounds; ++round) {
     const unsigned long long cand = (tid < TL && head < kKL) ? keys[tid * kKL + head] : 0ull;
     unsigned long long wb = cand;
 #pragma unroll
@@ -271,6 +274,12 @@ __global__ void __launch_bounds__(kMergeThreads) sa_merge_rescore_kernel(const M
     }
     if (cand == gb) ++head;  // keys of real candidates are unique (rows are unique per query)
     kth = gb;
+  }
+  if (p.bound_out != nullptr) {
+    // Sampling pre-pass: at least kKL rows of the corpus score >= the sample's kKL-th best, so no row scoring less can be
+    // in this query's global top-kKL: a valid shared threshold for the full scan that follows (same key as float_to_key).
+    if (tid == 0 && kth != 0ull) atomicMax(p.bound_out + q, static_cast<unsigned>(kth >> 32));
+    return;
   }
   const double qq = qq_s;
   // eps and band, rounded towards "wider"

@@ -75,7 +75,7 @@ struct ScanParams {
   int* part_idx;          // [gridDim.x][128][kKL]
   float* part_drop;       // [gridDim.x][128]  upper bound on the approximate score of the lane's rows not in the list
   int corpus_evict_first; // 1: corpus tiles are read by a single query block -> stream them through L2
-  int l2_prefetch;        // K slices the L2 prefetch stream runs ahead of the smem ring's TMA loads (0 = off)
+  int tile_stride;        // 1: walk every tile; S > 1: the sampling pre-pass walks tiles 0, S, 2S, ... only
   int* lane_progress;     // [tl_count][nqb] tiles whose loads each unit has issued (zero at launch), or nullptr
   int unit_map;           // 0: unit = tl*nqb + qb (lane-mates adjacent), 1: unit = qb*TL + tl (lane-mates TL apart)
   int max_drift;          // lead (in tiles) over the slowest lane-mate that is not paced
@@ -358,6 +358,7 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   const int nqb = p.nqb;  // units per tile lane
   const int qb = p.unit_map == 0 ? unit % nqb : unit / TL;
   const int tl = p.unit_map == 0 ? unit / nqb : unit % TL;
+  const int walk_tiles = (p.num_tiles + p.tile_stride - 1) / p.tile_stride;  // tiles this launch visits (all lanes together)
 
   // ------------------------------------------------------------------ one-time setup
   long long t_start = 0;
@@ -409,7 +410,8 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       int pace = 0;
       int tile_no = 0;
       const int q_row = qb * kRowsPerQb + static_cast<int>(rank) * kBlockM;
-      for (int t = tl; t < p.num_tiles; t += TL, ++tile_no) {
+      for (int ti = tl; ti < walk_tiles; ti += TL, ++tile_no) {
+        const int t = ti * p.tile_stride;
         if (lockstep) {
           const int* pr = p.lane_progress + tl * nqb;
           int slowest = tile_no;
@@ -428,18 +430,6 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             const long long c0 = clock64();
             while (clock64() - c0 < pace) {
             }
-          }
-          if (p.l2_prefetch > 0) {
-            // The smem ring holds 4 (6) K slices; HBM latency under load is longer than the ring lasts, so the ring
-            // alone leaves the MMA issuer starved while the producer waits for free slots.  Ask L2 for the slice
-            // `l2_prefetch` positions ahead: when its turn in the ring comes, the TMA load is an L2 hit.
-            int kb2 = kb + p.l2_prefetch, t2 = t;
-            while (kb2 >= p.num_kb) {
-              kb2 -= p.num_kb;
-              t2 += TL;
-            }
-            if (t2 < p.num_tiles)
-              tma_prefetch_l2_2d(&tmap_c, kb2 * kBlockK, t2 * kBlockN + static_cast<int>(rank) * Cfg::kBRows);
           }
           if constexpr (kCG == 1) {
             mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
@@ -471,7 +461,7 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       uint32_t phase = 0;
       int it = 0;
       long long w_full = 0, w_tempty = 0;
-      for (int t = tl; t < p.num_tiles; t += TL, ++it) {
+      for (int ti = tl; ti < walk_tiles; ti += TL, ++it) {
         const int a = it & 1;
         const uint32_t aph = (it >> 1) & 1u;
         if constexpr (kProf) {
@@ -546,17 +536,18 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         nx1 = make_float4(x[4], x[5], x[6], x[7]);
       }
     };
-    if (tl < p.num_tiles) fetch_ic(tl);
+    if (tl < walk_tiles) fetch_ic(tl * p.tile_stride);
 
     long long w_tfull = 0, busy = 0, slow_chunks = 0;
     int it = 0;
-    for (int t = tl; t < p.num_tiles; t += TL, ++it) {
+    for (int ti = tl; ti < walk_tiles; ti += TL, ++it) {
+      const int t = ti * p.tile_stride;
       const float qnan = __int_as_float(0x7fc00000);
       auto sc = [&](float x) { return x > 0.f ? x : qnan; };
       float4* dst = reinterpret_cast<float4*>(ic + 8 * lane);
       dst[0] = make_float4(sc(nx0.x), sc(nx0.y), sc(nx0.z), sc(nx0.w));
       dst[1] = make_float4(sc(nx1.x), sc(nx1.y), sc(nx1.z), sc(nx1.w));
-      if (t + TL < p.num_tiles) fetch_ic(t + TL);  // prefetch the next tile's inverse norms
+      if (ti + TL < walk_tiles) fetch_ic((ti + TL) * p.tile_stride);  // prefetch the next tile's inverse norms
       __syncwarp();                                // ic[] visible to the whole warp
       const int a = it & 1;
       const uint32_t aph = (it >> 1) & 1u;

@@ -138,13 +138,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(x), "r"(y), "l"(hint)
       : "memory");
 }
-// Prefetch one box of the tensor into L2 only (no smem destination, no mbarrier): used to run the HBM stream further
-// ahead of the smem ring than the ring itself can hold.
-__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int x, int y) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(x),
-               "r"(y)
-               : "memory");
-}
 // Same, issued by either CTA of an MMA pair: data lands in the issuing CTA's smem, completion bytes are
 // credited to the mbarrier at the same offset in the pair's leader (even) CTA.
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;

@@ -362,6 +362,41 @@ def test_scan_profile_counters(bf):
     ix.close()
 
 
+@pytest.mark.parametrize("cg", [1, 2])
+def test_sampling_prepass_keeps_answers_and_tames_an_ascending_corpus(bf, cg):
+    """Option "presample": a pre-pass over every S-th tile seeds the shared thresholds.  It may only move work around; and
+    on a corpus stored in ASCENDING order of similarity to the queries -- where without it every tile brings rows that
+    beat everything seen before -- it keeps the scan's time near the random-order time."""
+    import torch
+    from qsa_b200.engine import VectorIndex
+    dim, n, nq, k = 64, 400_000, 300, 10
+    g = np.random.default_rng(5)
+    centre = g.standard_normal(dim).astype(np.float32)
+    cf = g.standard_normal((n, dim)).astype(np.float32)
+    order = np.argsort(cf @ centre / np.linalg.norm(cf, axis=1))
+    qf = centre[None, :] + 0.3 * g.standard_normal((nq, dim)).astype(np.float32)
+    q = bf.f32_to_bf16_bits(qf)
+    times = {}
+    for name, rows in (("random", cf), ("ascending", cf[order])):
+        c = bf.f32_to_bf16_bits(rows)
+        ix = VectorIndex(dim=dim, capacity=n, max_batch=512, max_k=k)
+        ix.append_bf16_bits(c)
+        ix.set_option("cta_group", cg)
+        rs, ri = bf.cosine_topk_fast(q[:40], [(0, c)], k)
+        for ps in (0, 2, 8):
+            ix.set_option("presample", ps)
+            s, i = ix.search(dev(q), k)
+            torch.cuda.synchronize()
+            assert (i.cpu().numpy()[:40] == ri).all(), (name, ps)
+            for _ in range(5):
+                ix.search(dev(q), k)
+            torch.cuda.synchronize()
+            times[(name, ps)] = ix.timing_mean(5)[1]
+        ix.close()
+    assert times[("ascending", 8)] < 0.7 * times[("ascending", 0)], times      # the pre-pass removes the blow-up ...
+    assert times[("ascending", 8)] < 2.0 * times[("random", 0)], times         # ... to within 2x of the random order
+
+
 def test_drift_control_and_mapping_options_do_not_change_answers(bf):
     """Pacing, unit mapping and CTA grouping only move work around in time and space."""
     from qsa_b200.engine import VectorIndex
