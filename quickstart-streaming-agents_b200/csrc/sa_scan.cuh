@@ -199,7 +199,9 @@ struct TopList {
 // lowest row among equals), inserts it, masks it and re-reduces -- until nothing beats the threshold.  A warp executes
 // as many rounds as its busiest lane needs (usually one or two), however the qualifying values are spread over the 32
 // rows; walking the rows group by group instead costs a round per group that ANY lane has a hit in, which during the
-// warm-up of a short scan (1M rows: 26 tiles per lane) was most of the epilogue's time.
+// warm-up of a short scan (1M rows: 26 tiles per lane) was most of the epilogue's time (A/B on B200,
+// profiles/r02_ab_insertion_walk.json: epilogue 15.1k -> 9.6k cycles per tile at 1M x 1536 / batch 256, scan +7..15 %;
+// 7.3k -> 4.6k at 6.25M x 768 / batch 128; neutral at batch 1024).
 template <int kKL>
 __host__ __device__ __forceinline__ bool chunk_process(TopList<kKL>& L, float (&v)[kChunk], const float (&w)[kChunk],
                                                        int row_base) {
@@ -221,29 +223,6 @@ __host__ __device__ __forceinline__ bool chunk_process(TopList<kKL>& L, float (&
     L.drop = max_nn(L.drop, m);
     return false;
   }
-#ifdef SA_EPI_GROUPWISE  // A/B build of the round-1 style walk, group of four rows by group (tools/gpu_ab.sh)
-#ifdef __CUDA_ARCH__
-#pragma unroll
-#endif
-  for (int i = 0; i < 8; ++i) {
-    float s0 = v[4 * i], s1 = v[4 * i + 1], s2 = v[4 * i + 2], s3 = v[4 * i + 3];
-    float mg = max_nn(max_nn(s0, s1), max_nn(s2, s3));
-    while (mg > L.thr) {
-      const int j = (s0 == mg) ? 0 : (s1 == mg) ? 1 : (s2 == mg) ? 2 : 3;
-      const float sj = (j == 0) ? s0 : (j == 1) ? s1 : (j == 2) ? s2 : s3;
-      L.drop = max_nn(L.drop, L.sc[kKL - 1]);
-      list_insert<kKL>(L.sc, L.id, sj, row_base + 4 * i + j);
-      L.thr = max_nn(L.sc[kKL - 1], L.thr_floor);
-      s0 = (j == 0) ? -INFINITY : s0;
-      s1 = (j == 1) ? -INFINITY : s1;
-      s2 = (j == 2) ? -INFINITY : s2;
-      s3 = (j == 3) ? -INFINITY : s3;
-      mg = max_nn(max_nn(s0, s1), max_nn(s2, s3));
-    }
-    L.drop = max_nn(L.drop, mg);
-  }
-  return true;
-#endif
   do {
     int pos = kChunk - 1;
 #ifdef __CUDA_ARCH__

@@ -97,7 +97,10 @@ class Codec:
 class Lab2Pipeline:
     def __init__(self, log_dir: str, table: VectorTable, embedder=None, k: int = 3, max_batch: int = 1024,
                  group: str = "sa-lab2", generator=stub_generator, score_mode: str = "cosine", native: bool | None = None,
-                 metrics_file: str | None = None, metrics_every_s: float = 5.0):
+                 metrics_file: str | None = None, metrics_every_s: float = 5.0, transport=None, client_conf: dict | None = None):
+        """``transport``: a module with ``Producer`` / ``Consumer`` / ``TopicPartition`` -- ``transport.filelog`` (default,
+        topics are files under ``log_dir``) or ``transport.kafka`` (a real cluster through confluent_kafka; ``client_conf``
+        carries bootstrap.servers etc., ``log_dir`` then only holds the schema-registry stub)."""
         if score_mode not in ("cosine", "atlas"):
             raise ValueError("score_mode must be 'cosine' (raw) or 'atlas' ((1 + cos) / 2, what MongoDB Atlas reports)")
         self.log_dir = log_dir
@@ -108,11 +111,17 @@ class Lab2Pipeline:
         self.generator = generator
         self.score_mode = score_mode
         self.codec = Codec(log_dir)
-        self.producer = Producer({"log.dir": log_dir})
-        conf = {"log.dir": log_dir, "group.id": group, "auto.offset.reset": "earliest", "enable.auto.commit": False}
+        tp_mod = transport
+        if tp_mod is None:
+            from ..transport import filelog as tp_mod
+        TopicPartition = tp_mod.TopicPartition
+        base = dict(client_conf or {})
+        base["log.dir"] = log_dir
+        self.producer = tp_mod.Producer(base)
+        conf = dict(base, **{"group.id": group, "auto.offset.reset": "earliest", "enable.auto.commit": False})
         self.consumers = {}
         for t in ("documents", "documents_embed", "queries", "queries_embed", "search_results"):
-            c = Consumer(conf)
+            c = tp_mod.Consumer(conf)
             c.subscribe([t])
             self.consumers[t] = c
         # the sink reads from where the TABLE's content ends, not from where some earlier process committed
@@ -395,7 +404,8 @@ class Lab2Pipeline:
         """queries_embed -> VECTOR_SEARCH_AGG -> search_results.  When the index offers the split host call
         (``search_host_submit`` / ``search_host_wait``), batches are software-pipelined: batch i+1 is read and decoded
         while the GPU searches batch i.  Offsets of a batch are committed only after its results are flushed."""
-        if self._wire is not None and len(self.table) == self.table.arena_document_id.n:
+        if (self._wire is not None and len(self.table) == self.table.arena_document_id.n
+                and hasattr(self.consumers["queries_embed"], "consume_raw")):
             return self._stage_search_native()
         return self._stage_search_generic()
 

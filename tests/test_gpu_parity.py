@@ -369,7 +369,7 @@ def test_sampling_prepass_keeps_answers_and_tames_an_ascending_corpus(bf, cg):
     beat everything seen before -- it keeps the scan's time near the random-order time."""
     import torch
     from qsa_b200.engine import VectorIndex
-    dim, n, nq, k = 64, 400_000, 300, 10
+    dim, n, nq, k = 64, 520_000, 300, 10          # 2032 tiles: enough for a stride-8 sample on 49 (37) tile lanes
     g = np.random.default_rng(5)
     centre = g.standard_normal(dim).astype(np.float32)
     cf = g.standard_normal((n, dim)).astype(np.float32)

@@ -1,3 +1,4 @@
+import os
 """File-log transport: the Kafka semantics the reference's scripts and tests rely on."""
 import threading
 
@@ -84,3 +85,46 @@ def test_concurrent_producers_lose_nothing(tmp_path):
     for m in msgs:
         tag, i = m.key().decode().split("-")
         assert m.value() == b"d" * (int(i) % 50)
+
+
+def test_kafka_adapter_drives_the_same_pipeline(tmp_path, monkeypatch):
+    """transport.kafka (confluent_kafka behind the serve loop's transport interface) against an in-memory stand-in of
+    the library: the Lab2 graph produces the same `search_results` bytes as over the file log, the sink rebuilds the
+    table from the beginning of `documents_embed` whatever the group committed, and offsets are committed per batch."""
+    import sys
+
+    import numpy as np
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import fake_confluent_kafka as fck
+    from doubles import PipelinedOracleIndex
+    from qsa_b200.operator import VectorTable
+    from qsa_b200.pipeline.serve import Lab2Pipeline
+    from qsa_b200.transport import filelog, kafka
+    monkeypatch.setitem(sys.modules, "confluent_kafka", fck)
+    fck.reset()
+    g = np.random.default_rng(4)
+    dim = 32
+    docs = [(f"d{i}", f"chunk {i}", g.standard_normal(dim).astype(np.float32)) for i in range(40)]
+    queries = [(f"q{i}", g.standard_normal(dim).astype(np.float32)) for i in range(25)]
+    outs = {}
+    for name, mod, conf in (("file", filelog, None), ("kafka", kafka, {"bootstrap.servers": "fake:9092"})):
+        logd = str(tmp_path / name)
+        for attempt in range(2):                       # the second pipeline object = a restarted process, empty table
+            table = VectorTable(PipelinedOracleIndex(dim))
+            pipe = Lab2Pipeline(logd, table, k=3, max_batch=8, transport=mod, client_conf=conf)
+            if attempt == 0:
+                for d, c, v in docs:
+                    pipe.producer.produce("documents_embed", key=d, value=pipe.codec.encode(
+                        "documents_embed", {"document_id": d, "chunk": c, "embedding": v}))
+                pipe.producer.flush()
+            for q, v in queries[attempt * 12:(attempt + 1) * 12 + attempt]:
+                pipe.producer.produce("queries_embed", value=pipe.codec.encode("queries_embed", {"query": q, "embedding": v}))
+            pipe.producer.flush()
+            pipe.run_until_idle()
+            assert len(table) == 40                    # rebuilt from the log on the restart
+        c = mod.Consumer(dict(conf or {}, **{"log.dir": logd, "group.id": "check", "enable.auto.commit": False}))
+        c.subscribe(["search_results"])
+        outs[name] = [m.value() for m in c.consume(100, 0.0)]
+    assert len(outs["file"]) == 25 and outs["kafka"] == outs["file"]
+    assert fck._BROKER["groups"]["sa-lab2"][("queries_embed", 0)] == 25

@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--batches", default="128,1024")
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--presample", default="0,64", help="values of the engine option to compare")
+    ap.add_argument("--noise", type=float, default=0.6, help="spread of the queries around their centroid (0.1 = near-duplicates)")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     n, dim, k = a.rows, a.dim, a.k
@@ -86,7 +87,7 @@ def main():
 
     for B in [int(x) for x in a.batches.split(",")]:
         centre = torch.randn(dim, generator=g, device=dev)
-        q_near = (centre[None, :] + 0.6 * torch.randn((B, dim), generator=g, device=dev)).to(torch.bfloat16)
+        q_near = (centre[None, :] + a.noise * torch.randn((B, dim), generator=g, device=dev)).to(torch.bfloat16)
         cases = []
         # ---- iid rows, queries clustered around `centre`: random order, then ascending similarity to the centroid
         fill(lambda: None, "iid")
@@ -120,7 +121,7 @@ def main():
         # ---- clustered embeddings stored cluster by cluster
         fill(lambda: None, "clustered")
         q_c = (ix.rows[torch.randint(0, n, (B,), generator=g, device=dev)].float() +
-               0.5 * torch.randn((B, dim), generator=g, device=dev)).to(torch.bfloat16)
+               a.noise * torch.randn((B, dim), generator=g, device=dev)).to(torch.bfloat16)
         base = {}
         for ps in [int(x) for x in a.presample.split(",")]:
             ix.set_option("presample", ps)
