@@ -39,11 +39,12 @@ def stage_dots(cg, n=1024, dim=1536, nq=128):
     return ok
 
 
-def stage_search(cg, n=20000, dim=1536, nq=200, k=10):
+def stage_search(cg, n=20000, dim=1536, nq=200, k=10, force_fix=0):
     c = bf.synth_rows(1234, 0, n, dim)
     q = bf.synth_queries(4321, nq, dim, c)
     ix = VectorIndex(dim=dim, capacity=n + 1000, max_batch=max(nq, 256), max_k=max(k, 10))
     ix.set_option("cta_group", cg)
+    ix.set_option("force_fix", force_fix)      # 1: every (query, lane) also goes through the exact fallback scan
     ix.append_bf16_bits(c)
     s, i = ix.search(bits_to_dev(q), k)
     torch.cuda.synchronize()

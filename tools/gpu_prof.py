@@ -26,6 +26,7 @@ SHAPES = {
     "b1024": (10_000_000, 1536, 1024, 10), # config 3, headline
     "cfg2": (1_000_000, 1536, 256, 10),    # config 2
     "cfg4": (1_250_000, 1536, 4096, 10),   # config 4, one of 8 shards
+    "n8shard": (1_250_000, 1536, 1024, 10),  # the headline batch on one of 8 shards
     "b256": (10_000_000, 1536, 256, 10),
     "b512": (10_000_000, 1536, 512, 10),
 }
@@ -97,6 +98,7 @@ def main():
             "shape": name, "rows": n, "dim": dim, "batch": B, "k": k, "grid": ix.info("last_grid"), "launches": t.launches,
             "scan_ms": scan_ms, "total_ms": total_ms, "tail_ms": total_ms - scan_ms, "gbs": gbs, "tflops": tfs,
             "cycles_per_tile": per_tile(p["total"]),
+            "cta_cycles_min_max": [int(p["total"][lead].min()), int(p["total"][lead].max())] if lead.any() else None,
             "prod_wait_empty": per_tile(p["prod_wait_empty"]),
             "mma_wait_full": per_tile(p["mma_wait_full"], issuer), "mma_wait_tempty": per_tile(p["mma_wait_tempty"], issuer),
             "epi_wait_tfull": per_tile(p["epi_wait_tfull"]), "epi_busy": per_tile(p["epi_busy"]),
