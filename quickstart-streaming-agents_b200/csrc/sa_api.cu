@@ -192,6 +192,17 @@ struct sa_engine {
 
 namespace {
 
+int launch_merge_packed(const sa::PackedHit* hits, int n_shards, int nq, int k, float* out_score, long long* out_row,
+                        cudaStream_t st) {
+  if (n_shards <= 32 && n_shards * k <= 256 && k <= sa::kMergePackedMaxK)
+    sa::sa_merge_packed_kernel<<<(nq + sa::kMergePackedWarps - 1) / sa::kMergePackedWarps, sa::kMergePackedWarps * 32, 0, st>>>(
+        hits, n_shards, nq, k, out_score, out_row);
+  else
+    sa::sa_merge_packed_serial_kernel<<<(nq + 127) / 128, 128, 0, st>>>(hits, n_shards, nq, k, out_score, out_row);
+  SA_CUDA(cudaGetLastError());
+  return SA_OK;
+}
+
 struct LaunchPlan {
   int cg;
   int q0;   // first query of this launch
@@ -931,8 +942,8 @@ int sharded_search_on_stream(sa_comm* c, int local, sa_engine* e, const uint16_t
     SA_NCCL(g_nccl.AllGather(e->hits, gathered, bytes, ncclChar, c->comms[local], st));
   }
   if (phases & 4) {
-    sa::sa_merge_packed_kernel<<<(nq + 127) / 128, 128, 0, st>>>(gathered, c->n_ranks, nq, k, out_score_dev, out_row_dev);
-    SA_CUDA(cudaGetLastError());
+    rc = launch_merge_packed(gathered, c->n_ranks, nq, k, out_score_dev, out_row_dev, st);
+    if (rc) return rc;
     e->ring[(e->n_searches - 1) % kTimingRing].kernels += 2;  // the collective and the shard merge
   }
   return SA_OK;
@@ -1070,11 +1081,8 @@ int sa_merge_hits(sa_engine* e, const sa_hit* hits_dev, int n_shards, int nq, in
   if (n_shards <= 0 || n_shards > 64) return fail(SA_ERR_ARG, "n_shards %d outside [1, 64]", n_shards);
   if (nq <= 0 || k <= 0) return fail(SA_ERR_ARG, "nq and k must be positive");
   SA_ON_DEVICE(e->device);
-  sa::sa_merge_packed_kernel<<<(nq + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const sa::PackedHit*>(hits_dev), n_shards, nq, k, out_score_dev,
-      reinterpret_cast<long long*>(out_row_dev));
-  SA_CUDA(cudaGetLastError());
-  return SA_OK;
+  return launch_merge_packed(reinterpret_cast<const sa::PackedHit*>(hits_dev), n_shards, nq, k, out_score_dev,
+                             reinterpret_cast<long long*>(out_row_dev), reinterpret_cast<cudaStream_t>(stream));
 }
 
 // ---- communicator ---------------------------------------------------------------------------------------------------

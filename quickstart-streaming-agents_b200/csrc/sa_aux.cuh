@@ -352,9 +352,9 @@ __global__ void __launch_bounds__(kMergeThreads) sa_merge_rescore_kernel(const M
 //
 // Work item = (queue entry, chunk of kFixChunkTiles tiles of that lane).  A CTA stages the query (fp32) in shared memory;
 // each warp walks rows: fp32 dot (CUDA cores) * 1/|c| -> a'(r), whose error is far inside eps; rows with a' >= max(band,
-// current k-th exact cosine in approximate units - eps) are re-scored exactly and inserted into the CTA's list; at the
-// end of the item the CTA folds its list into the query's result under the query's lock (rows already present are
-// skipped).  The last CTA to finish finalises.
+// current k-th exact cosine in approximate units - eps) are re-scored exactly and inserted into the WARP's own list (no
+// sharing between warps, so no locks in shared memory); at the end of the item one thread folds the warps' lists into the
+// query's result under the query's lock (rows already present are skipped).  The last CTA to finish finalises.
 // ------------------------------------------------------------------------------------------------------------------
 struct PackedHit {
   double score;       // cosine, float64
@@ -433,10 +433,10 @@ __device__ __forceinline__ void fix_list_insert(D* cosv, I* rowv, int k, double 
 
 __global__ void __launch_bounds__(kFixThreads) sa_fixup_kernel(const FixParams p) {
   extern __shared__ float4 fix_smem[];  // query as fp32: [dim/8] float4 "lo" halves, then [dim/8] "hi" halves
-  __shared__ double l_cos[kFixMaxK];
-  __shared__ int l_row[kFixMaxK];
-  __shared__ int l_lock;
-  __shared__ float thr_s;
+  constexpr int kWarps = kFixThreads / 32;
+  __shared__ double l_cos[kWarps][kFixMaxK];  // one list per warp, touched by that warp's lane 0 only
+  __shared__ int l_row[kWarps][kFixMaxK];
+  __shared__ float thr0_s;
   __shared__ int last_s;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -472,24 +472,26 @@ __global__ void __launch_bounds__(kFixThreads) sa_fixup_kernel(const FixParams p
       q_hi[i] = make_float4(bf16_bits_to_f32(x.z & 0xffffu), bf16_bits_to_f32(x.z >> 16), bf16_bits_to_f32(x.w & 0xffffu),
                             bf16_bits_to_f32(x.w >> 16));
     }
-    if (tid < kFixMaxK) {
-      l_cos[tid] = -INFINITY;
-      l_row[tid] = -1;
+    for (int i = tid; i < kWarps * kFixMaxK; i += kFixThreads) {
+      l_cos[i / kFixMaxK][i % kFixMaxK] = -INFINITY;
+      l_row[i / kFixMaxK][i % kFixMaxK] = -1;
     }
     if (tid == 0) {
-      l_lock = 0;
       // prefilter threshold: the band of the merge kernel, tightened by the k-th exact cosine found so far
       float thr = fq->band;
       const int rk = g_row[p.k - 1];
       if (rk >= 0) thr = fmaxf(thr, __fsub_rd(__double2float_rd(g_cos[p.k - 1] * qn), eps));
-      thr_s = thr;
+      thr0_s = thr;
     }
     __syncthreads();
+    float thr = thr0_s;           // per warp from here on: tightened by the warp's own list (uniform across its lanes)
+    double* wc = l_cos[warp];
+    int* wr = l_row[warp];
 
     for (int ti = 0; ti < kFixChunkTiles; ++ti) {
       const int t = t_first + ti * TL;
       if (t >= p.num_tiles) break;
-      for (int rr = warp; rr < 256; rr += kFixThreads / 32) {
+      for (int rr = warp; rr < 256; rr += kWarps) {
         const long long r = static_cast<long long>(t) * 256 + rr;
         if (r >= p.n_rows) break;
         const float inv = __ldg(p.inv_norm + r);
@@ -510,37 +512,29 @@ __global__ void __launch_bounds__(kFixThreads) sa_fixup_kernel(const FixParams p
         }
         acc = warp_sum(acc);
         const float ap = acc * inv;
-        const float thr = *reinterpret_cast<volatile float*>(&thr_s);
         if (!(ap >= thr)) continue;  // warp-uniform (every lane holds the same sum)
         const double c = exact_cosine_warp(qv, cv, nvec, qq, lane);
+        float nt = thr;
         if (lane == 0) {
-          const int ri = static_cast<int>(r);
-          volatile double* lc = l_cos;
-          volatile int* lr = l_row;
-          const int tail_row = lr[p.k - 1];
-          if (tail_row < 0 || result_before(c, ri, lc[p.k - 1], tail_row)) {
-            while (atomicCAS(&l_lock, 0, 1) != 0) {
-            }
-            __threadfence_block();
-            fix_list_insert(lc, lr, p.k, c, ri);
-            if (lr[p.k - 1] >= 0) {
-              const float nt = __fsub_rd(__double2float_rd(lc[p.k - 1] * qn), eps);
-              if (nt > thr_s) *reinterpret_cast<volatile float*>(&thr_s) = nt;
-            }
-            __threadfence_block();
-            atomicExch(&l_lock, 0);
-          }
+          fix_list_insert(wc, wr, p.k, c, static_cast<int>(r));
+          if (wr[p.k - 1] >= 0) nt = fmaxf(thr, __fsub_rd(__double2float_rd(wc[p.k - 1] * qn), eps));
         }
+        thr = __shfl_sync(0xffffffffu, nt, 0);
       }
     }
     __syncthreads();
-    if (tid == 0 && l_row[0] >= 0) {
-      while (atomicCAS(&fq->lock, 0, 1) != 0) {
+    if (tid == 0) {  // fold the warps' lists into the query's result under its lock (rows already present are skipped)
+      bool any = false;
+      for (int w = 0; w < kWarps; ++w) any = any || l_row[w][0] >= 0;
+      if (any) {
+        while (atomicCAS(&fq->lock, 0, 1) != 0) {
+        }
+        __threadfence();
+        for (int w = 0; w < kWarps; ++w)
+          for (int i = 0; i < p.k && l_row[w][i] >= 0; ++i) fix_list_insert(g_cos, g_row, p.k, l_cos[w][i], l_row[w][i]);
+        __threadfence();
+        atomicExch(&fq->lock, 0);
       }
-      __threadfence();
-      for (int i = 0; i < p.k && l_row[i] >= 0; ++i) fix_list_insert(g_cos, g_row, p.k, l_cos[i], l_row[i]);
-      __threadfence();
-      atomicExch(&fq->lock, 0);
     }
   }
 
@@ -562,9 +556,57 @@ __global__ void __launch_bounds__(kFixThreads) sa_fixup_kernel(const FixParams p
 }
 
 // After the all-gather of the packed per-shard results: per query, merge G shard lists of k (already sorted, global
-// rows) into the global top-k by (cosine desc, global row asc).  One thread per query; G*k <= a few hundred.
-__global__ void sa_merge_packed_kernel(const PackedHit* __restrict__ hits, int n_shards, int nq, int k,
-                                       float* __restrict__ out_score, long long* __restrict__ out_idx) {
+// rows) into the global top-k by (cosine desc, global row asc).  One warp per query, lane g holds the head of shard g's
+// list (G <= 32): k rounds of a warp arg-max, the winning lane advances.  The lists are first staged in shared memory
+// with coalesced 16-byte loads.
+constexpr int kMergePackedWarps = 4;
+constexpr int kMergePackedMaxK = 32;
+__global__ void __launch_bounds__(kMergePackedWarps * 32)
+sa_merge_packed_kernel(const PackedHit* __restrict__ hits, int n_shards, int nq, int k, float* __restrict__ out_score,
+                       long long* __restrict__ out_idx) {
+  __shared__ PackedHit stage[kMergePackedWarps][32 * kMergePackedMaxK / 4];  // n_shards * k <= 256 hits per query
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * kMergePackedWarps + warp;
+  if (q >= nq) return;
+  PackedHit* mine = stage[warp];
+  const int per = k;  // hits of one shard for this query
+  for (int i = lane; i < n_shards * per; i += 32) {
+    const int g = i / per, j = i % per;
+    mine[i] = hits[(static_cast<size_t>(g) * nq + q) * k + j];
+  }
+  __syncwarp();
+  int head = 0;
+  for (int i = 0; i < k; ++i) {
+    double s = -INFINITY;
+    long long r = -1;
+    if (lane < n_shards && head < k) {
+      const PackedHit h = mine[lane * per + head];
+      s = h.score;
+      r = h.row;
+    }
+    // warp arg-max by (score desc, row asc); lanes without a candidate carry r = -1
+    double bs = s;
+    long long br = r;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double os = __shfl_xor_sync(0xffffffffu, bs, o);
+      const long long orow = __shfl_xor_sync(0xffffffffu, br, o);
+      const bool take = orow >= 0 && (br < 0 || os > bs || (os == bs && orow < br));
+      bs = take ? os : bs;
+      br = take ? orow : br;
+    }
+    if (r >= 0 && r == br) ++head;  // global rows are unique: exactly one lane advances
+    if (lane == 0) {
+      const size_t oo = static_cast<size_t>(q) * k + i;
+      out_score[oo] = br >= 0 ? static_cast<float>(bs) : -INFINITY;
+      out_idx[oo] = br;
+    }
+  }
+}
+
+// The same merge for any number of shards (one thread per query); used when n_shards > 32 or n_shards * k > 256.
+__global__ void sa_merge_packed_serial_kernel(const PackedHit* __restrict__ hits, int n_shards, int nq, int k,
+                                              float* __restrict__ out_score, long long* __restrict__ out_idx) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nq) return;
   int head[64];

@@ -29,7 +29,7 @@ constexpr int kBlockM = 128;  // queries per CTA  (TMEM lanes)
 constexpr int kBlockN = 256;  // corpus rows per tile (TMEM columns per accumulator)
 constexpr int kBlockK = 64;   // bf16 per K slice = 128 B = one swizzle atom
 constexpr int kUmmaK = 16;
-constexpr int kScanThreads = 256;  // w0 corpus TMA, w1 MMA, w2 TMEM alloc, w3 query TMA, w4..7 epilogue
+constexpr int kScanThreads = 256;  // w0 TMA, w1 MMA, w2 TMEM alloc, w3 idle, w4..7 epilogue
 constexpr int kTmemCols = 512;
 constexpr int kChunk = 32;         // TMEM columns per tcgen05.ld
 
@@ -38,29 +38,22 @@ constexpr int kModeProd = 0;   // production
 constexpr int kModeDots = 1;   // test hook: also dump the raw accumulators of one tile
 constexpr int kModeProf = 2;   // profiling: per-role wait / busy cycle counters (ScanParams::prof)
 
-// Shared-memory rings.  The query slices (re-read for every tile, always L2 hits) and the corpus slices (each read once,
-// the first reader of a tile takes an HBM miss) have separate rings with separate producers: with one combined ring the
-// corpus -- the only operand whose latency matters -- got 4 (6) slices of run-ahead; decoupled it gets 5 (9) in the
-// same 208 KB, because the Q ring can be short.
 template <int kCG>
 struct ScanCfg {
-  static constexpr int kStagesA = (kCG == 1) ? 3 : 4;   // Q slices   [128 x 64] bf16 = 16 KB
-  static constexpr int kStagesB = (kCG == 1) ? 5 : 9;   // corpus slices [256/kCG x 64] bf16 = 32 / 16 KB
+  static constexpr int kStages = (kCG == 1) ? 4 : 6;
   static constexpr int kBRows = kBlockN / kCG;  // corpus rows staged by each CTA
   static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
   static constexpr uint32_t kBBytes = kBRows * kBlockK * 2;
-  static constexpr uint32_t kRingBytes = kStagesA * kABytes + kStagesB * kBBytes;
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kIcBytes = 4 * kBlockN * sizeof(float);  // one 256-float scale vector per epilogue warp
-  static constexpr int kNumBars = 2 * kStagesA + 2 * kStagesB + 4;
-  static constexpr uint32_t kBarBytes = kNumBars * 8 + 16;
+  static constexpr uint32_t kBarBytes = (2 * kStages + 4) * 8 + 16;
   // +1024: the dynamic smem base is aligned up to 1024 B by hand (SWIZZLE_128B requirement).
-  static constexpr uint32_t kSmemBytes = kRingBytes + kIcBytes + kBarBytes + 1024;
-  static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kIcBytes + kBarBytes + 1024;
 };
 
 // Per-CTA profile record (kModeProf): SM cycles, summed over the kernel.
 struct ScanProf {
-  long long prod_wait_empty;   // corpus TMA producer blocked on a free smem slot
+  long long prod_wait_empty;   // TMA producer blocked on a free smem slot
   long long mma_wait_full;     // MMA issuer blocked on TMA data
   long long mma_wait_tempty;   // MMA issuer blocked on the epilogue (accumulator not drained)
   long long epi_wait_tfull;    // epilogue warp 0 blocked on the MMA (accumulator not complete)
@@ -317,7 +310,7 @@ __global__ void __launch_bounds__(kScanThreads, 1)
 sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                const ScanParams p) {
   using Cfg = ScanCfg<kCG>;
-  constexpr int kSA = Cfg::kStagesA, kSB = Cfg::kStagesB;
+  constexpr int kStages = Cfg::kStages;
   constexpr int kRowsPerQb = kBlockM * kCG;
   constexpr bool kProf = (kMode == kModeProf);
 
@@ -325,17 +318,16 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
-  float* icbuf = reinterpret_cast<float*>(smem_gen + Cfg::kRingBytes);  // [4 warps][256]
-  const uint32_t bar_base = smem_base + Cfg::kRingBytes + Cfg::kIcBytes;
-  auto fullA = [&](int s) { return bar_base + 8u * s; };
-  auto emptyA = [&](int s) { return bar_base + 8u * (kSA + s); };
-  auto fullB = [&](int s) { return bar_base + 8u * (2 * kSA + s); };
-  auto emptyB = [&](int s) { return bar_base + 8u * (2 * kSA + kSB + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kSA + 2 * kSB + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kSA + 2 * kSB + 2 + a); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + Cfg::kRingBytes + Cfg::kIcBytes + Cfg::kNumBars * 8);
-  auto a_smem = [&](int s) { return smem_base + kSB * Cfg::kBBytes + s * Cfg::kABytes; };  // B ring first: 1024-aligned either way
-  auto b_smem = [&](int s) { return smem_base + s * Cfg::kBBytes; };
+  float* icbuf = reinterpret_cast<float*>(smem_gen + kStages * Cfg::kStageBytes);  // [4 warps][256]
+  const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes + Cfg::kIcBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + kStages * Cfg::kStageBytes + Cfg::kIcBytes +
+                                                    (2 * kStages + 4) * 8);
+  auto a_smem = [&](int s) { return smem_base + s * Cfg::kStageBytes; };
+  auto b_smem = [&](int s) { return smem_base + s * Cfg::kStageBytes + Cfg::kABytes; };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -356,13 +348,9 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     tma_prefetch_desc(&tmap_c);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kSA; ++s) {
-      mbar_init(fullA(s), 1);   // the (leader) producer's arrive.expect_tx; TMA bytes complete it
-      mbar_init(emptyA(s), 1);  // one tcgen05.commit per use
-    }
-    for (int s = 0; s < kSB; ++s) {
-      mbar_init(fullB(s), 1);
-      mbar_init(emptyB(s), 1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);   // the (leader) producer's arrive.expect_tx; TMA bytes complete it
+      mbar_init(empty_bar(s), 1);  // one tcgen05.commit per use
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);         // tcgen05.commit after an accumulator's last MMA
@@ -383,7 +371,7 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   // ------------------------------------------------------------------ roles
   if (warp == 0) {
     if (lane == 0) {
-      // ===== corpus TMA producer =====
+      // ===== TMA producer =====
       const uint64_t c_hint = p.corpus_evict_first ? kEvictFirst : kEvictNormal;
       int stage = 0;
       uint32_t phase = 0;
@@ -400,6 +388,7 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       const bool lockstep = p.lane_progress != nullptr && p.pace_gain > 0 && nqb > 1 && rank == 0;
       int pace = 0;
       int tile_no = 0;
+      const int q_row = qb * kRowsPerQb + static_cast<int>(rank) * kBlockM;
       for (int ti = tl; ti < walk_tiles; ti += TL, ++tile_no) {
         const int t = ti * p.tile_stride;
         if (lockstep) {
@@ -411,10 +400,10 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         for (int kb = 0; kb < p.num_kb; ++kb) {
           if constexpr (kProf) {
             const long long c0 = clock64();
-            mbar_wait(emptyB(stage), phase ^ 1u);
+            mbar_wait(empty_bar(stage), phase ^ 1u);
             waited += clock64() - c0;
           } else {
-            mbar_wait(emptyB(stage), phase ^ 1u);
+            mbar_wait(empty_bar(stage), phase ^ 1u);
           }
           if (pace > 0) {
             const long long c0 = clock64();
@@ -422,14 +411,16 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             }
           }
           if constexpr (kCG == 1) {
-            mbar_expect_tx(fullB(stage), Cfg::kBBytes);
-            tma_load_2d(b_smem(stage), &tmap_c, fullB(stage), kb * kBlockK, t * kBlockN, c_hint);
+            mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+            tma_load_2d(a_smem(stage), &tmap_q, full_bar(stage), kb * kBlockK, q_row, kEvictLast);
+            tma_load_2d(b_smem(stage), &tmap_c, full_bar(stage), kb * kBlockK, t * kBlockN, c_hint);
           } else {
-            if (rank == 0) mbar_expect_tx(fullB(stage), 2 * Cfg::kBBytes);
-            tma_load_2d_pair(b_smem(stage), &tmap_c, fullB(stage), kb * kBlockK,
+            if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+            tma_load_2d_pair(a_smem(stage), &tmap_q, full_bar(stage), kb * kBlockK, q_row, kEvictLast);
+            tma_load_2d_pair(b_smem(stage), &tmap_c, full_bar(stage), kb * kBlockK,
                              t * kBlockN + static_cast<int>(rank) * Cfg::kBRows, c_hint);
           }
-          if (++stage == kSB) {
+          if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
           }
@@ -445,8 +436,8 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     if (lane == 0 && rank == 0) {
       // ===== MMA issuer (leader CTA of a pair) =====
       constexpr uint32_t idesc = make_idesc_bf16_f32(kBlockM * kCG, kBlockN);
-      int stage = 0, sa = 0;
-      uint32_t phase = 0, pa = 0;
+      int stage = 0;
+      uint32_t phase = 0;
       int it = 0;
       long long w_full = 0, w_tempty = 0;
       for (int ti = tl; ti < walk_tiles; ti += TL, ++it) {
@@ -462,29 +453,23 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(a * kBlockN);
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(fullA(sa), pa);  // the Q slice (an L2 hit, issued by its own producer: normally there already)
           if constexpr (kProf) {
             const long long c0 = clock64();
-            mbar_wait(fullB(stage), phase);
+            mbar_wait(full_bar(stage), phase);
             w_full += clock64() - c0;
           } else {
-            mbar_wait(fullB(stage), phase);
+            mbar_wait(full_bar(stage), phase);
           }
           tc_fence_after();
-          const uint64_t a_desc = make_kmajor_sw128_desc(a_smem(sa));
+          const uint64_t a_desc = make_kmajor_sw128_desc(a_smem(stage));
           const uint64_t b_desc = make_kmajor_sw128_desc(b_smem(stage));
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // +32 B along K inside the 128-B swizzle atom = +2 in the (addr >> 4) field
             umma_bf16<kCG>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit<kCG>(emptyA(sa));     // both commits fire when these MMAs retire: the two slots are free
-          umma_commit<kCG>(emptyB(stage));  // (in both CTAs of a pair)
-          if (++sa == kSA) {
-            sa = 0;
-            pa ^= 1u;
-          }
-          if (++stage == kSB) {
+          umma_commit<kCG>(empty_bar(stage));  // frees the smem slot (in both CTAs) once these MMAs retire
+          if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
           }
@@ -494,29 +479,6 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       if constexpr (kProf) {
         p.prof[blockIdx.x].mma_wait_full = w_full;
         p.prof[blockIdx.x].mma_wait_tempty = w_tempty;
-      }
-    }
-  } else if (warp == 3) {
-    if (lane == 0) {
-      // ===== query TMA producer: the same slice sequence as the corpus producer, through its own short ring =====
-      int stage = 0;
-      uint32_t phase = 0;
-      const int q_row = qb * kRowsPerQb + static_cast<int>(rank) * kBlockM;
-      for (int ti = tl; ti < walk_tiles; ti += TL) {
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(emptyA(stage), phase ^ 1u);
-          if constexpr (kCG == 1) {
-            mbar_expect_tx(fullA(stage), Cfg::kABytes);
-            tma_load_2d(a_smem(stage), &tmap_q, fullA(stage), kb * kBlockK, q_row, kEvictLast);
-          } else {
-            if (rank == 0) mbar_expect_tx(fullA(stage), 2 * Cfg::kABytes);
-            tma_load_2d_pair(a_smem(stage), &tmap_q, fullA(stage), kb * kBlockK, q_row, kEvictLast);
-          }
-          if (++stage == kSA) {
-            stage = 0;
-            phase ^= 1u;
-          }
-        }
       }
     }
   } else if (warp >= 4) {

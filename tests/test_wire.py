@@ -200,3 +200,47 @@ def test_all_30873_reference_records_roundtrip_bit_exactly():
             n += 1
     assert n == 30873 and parts == {0, 1, 2, 3, 4, 5}
     assert min(ts) == 1770605800879 and max(ts) == 1770692619057      # the 24.1 h span SURVEY.md appendix C records
+
+
+def test_native_batch_codecs_roundtrip_and_errors(lib):
+    """include/sa_wire.h directly: encode -> split -> decode round trip of queries_embed batches, byte equality with the
+    generic codec, and the error paths (truncated slice, short output buffer, foreign schema id)."""
+    import ctypes as C
+    from qsa_b200 import capi
+    from qsa_b200.wire import avro, schemas
+    g = np.random.default_rng(21)
+    n, dim, sid = 37, 96, 100123
+    texts = [("q%d é" % i).encode() if i % 5 else b"" for i in range(n)]
+    tbuf = b"".join(texts)
+    tlen = np.array([len(t) for t in texts], np.uint32)
+    toff = np.concatenate([[0], np.cumsum(tlen[:-1], dtype=np.uint64)]).astype(np.uint64)
+    vec = g.standard_normal((n, dim)).astype(np.float32)
+    rec_off = np.empty(n + 1, np.uint64)
+    need = C.c_uint64()
+    args = (n, dim, sid, tbuf, toff.ctypes.data, tlen.ctypes.data, vec.ctypes.data, 1234567)
+    assert lib.sa_wire_encode_queries_embed(*args, None, 0, rec_off.ctypes.data, C.byref(need)) == capi.SA_ERR_CAPACITY
+    out = np.empty(int(need.value), np.uint8)
+    assert lib.sa_wire_encode_queries_embed(*args, out.ctypes.data, out.size - 1, rec_off.ctypes.data, C.byref(need)) == capi.SA_ERR_CAPACITY
+    assert lib.sa_wire_encode_queries_embed(*args, out.ctypes.data, out.size, rec_off.ctypes.data, C.byref(need)) == 0
+    data = out.tobytes()
+    # the values are what the generic codec writes
+    cs = avro.CompiledSchema(schemas.TOPIC_SCHEMAS["queries_embed"])
+    voff = np.empty(n, np.uint64); vlen = np.empty(n, np.uint32); ts = np.empty(n, np.int64)
+    koff = np.empty(n, np.uint64); klen = np.empty(n, np.uint32)
+    assert lib.sa_wire_split_log(data, len(data), n, voff.ctypes.data, vlen.ctypes.data, koff.ctypes.data, klen.ctypes.data, ts.ctypes.data) == 0
+    assert (ts == 1234567).all() and (klen == 0xFFFFFFFF).all()
+    for i in range(n):
+        want = cs.encode({"query": texts[i].decode(), "embedding": vec[i]}, prefix=avro.frame(sid, b""))
+        assert data[int(voff[i]):int(voff[i]) + int(vlen[i])] == want
+    assert lib.sa_wire_split_log(data, len(data) - 3, n, voff.ctypes.data, vlen.ctypes.data, None, None, None) == capi.SA_ERR_ARG
+    assert b"truncated" in lib.sa_last_error()
+    # decode: all fast; with a foreign schema id: all handed to the generic path, rows zeroed
+    got = np.full((n, dim), 7.0, np.float32); to2 = np.empty(n, np.uint64); tl2 = np.empty(n, np.uint32)
+    st = np.empty(n, np.uint8); n_ok = C.c_int()
+    assert lib.sa_wire_decode_queries_embed(data, voff.ctypes.data, vlen.ctypes.data, n, dim, sid, got.ctypes.data,
+                                            to2.ctypes.data, tl2.ctypes.data, st.ctypes.data, C.byref(n_ok)) == 0
+    assert n_ok.value == n and (st == 0).all() and (got == vec).all()
+    assert [data[int(o):int(o) + int(l)] for o, l in zip(to2, tl2)] == texts
+    assert lib.sa_wire_decode_queries_embed(data, voff.ctypes.data, vlen.ctypes.data, n, dim, sid + 1, got.ctypes.data,
+                                            to2.ctypes.data, tl2.ctypes.data, st.ctypes.data, C.byref(n_ok)) == 0
+    assert n_ok.value == 0 and (st == 1).all() and (got == 0).all()
