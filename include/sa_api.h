@@ -36,7 +36,7 @@ typedef enum sa_status {
   SA_ERR_DEVICE = -5    /* device is not compute capability 10.x */
 } sa_status;
 
-#define SA_MAX_K 28 /* candidate lists hold 16 (k <= 12) or 32 entries per tile lane */
+#define SA_MAX_K 28 /* candidate lists hold 16 (k <= 16) or 32 entries per tile lane */
 #define SA_HOST_SLOTS 2 /* host-buffer searches that may be in flight at once (sa_search_host_submit) */
 
 int sa_version(void);

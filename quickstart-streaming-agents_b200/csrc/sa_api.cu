@@ -349,7 +349,9 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
   if (reinterpret_cast<uintptr_t>(q_bf16) % 16) return fail(SA_ERR_ARG, "query buffer must be 16-byte aligned");
   SA_ON_DEVICE(e->device);
 
-  const int kl = e->opt_list_len ? e->opt_list_len : ((k + 4 <= 16) ? 16 : 32);
+  // 16-entry lists for k <= 16: with the certificate any k <= kKL is exact; a margin of spare entries only makes the
+  // fallback rarer, and it is already rare once a tile lane holds more than a few thousand rows
+  const int kl = e->opt_list_len ? e->opt_list_len : (k <= 16 ? 16 : 32);
   if (k > kl) return fail(SA_ERR_ARG, "k %d needs candidate lists longer than list_len %d", k, kl);
   const int64_t n_rows = e->n_rows;
   const int num_tiles = static_cast<int>((n_rows + sa::kBlockN - 1) / sa::kBlockN);

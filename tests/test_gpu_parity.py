@@ -46,7 +46,9 @@ def bf():
     (5000, 768, 37, 5),        # config-5 shape (768-d, top-5)
     (256, 64, 1, 1),           # one tile, one query
     (257, 128, 129, 3),        # one row into the second tile; one query into the second block
-    (70000, 256, 300, 12),     # more tiles than tile lanes; k at the 16-entry list limit (k + 4)
+    (70000, 256, 300, 12),     # more tiles than tile lanes
+    (70000, 256, 300, 16),     # k == the 16-entry list length: every spare entry gone, still exact (certificate)
+    (2000, 256, 40, 16),       # ... with very few rows per lane (the fallback scan does the work)
     (9000, 192, 64, 28),       # 32-entry candidate lists, SA_MAX_K
 ])
 def test_search_matches_oracle(bf, cg, n, dim, nq, k):
