@@ -31,14 +31,24 @@ int sa_wire_split_log(const uint8_t* buf, uint64_t buf_len, int n, uint64_t* val
 
 /* Batch decode of queries_embed values.  For record i (value bytes buf[value_off[i] .. +value_len[i])):
  *   status[i] = 0  decoded: out_vec[i*dim .. +dim) holds the embedding, text_off/text_len[i] the UTF-8 query inside buf
- *               1  valid framing but an unusual shape (null query / null embedding / null item / multi-block array /
- *                  other schema id): hand the record to the generic codec
- *               2  poison (bad magic, truncated, wrong length, non-finite value): quarantine
+ *               1  anything else -- an unusual but legal shape (null query / null embedding / multi-block array / other
+ *                  schema id) or a bad record (bad magic, truncated, null item, wrong length, non-finite value): hand it
+ *                  to the generic codec, which decodes it or names the reason it is quarantined for
  * Rows of out_vec belonging to records with status != 0 are zero-filled.  Returns the number of status-0 records
  * through *n_ok. */
 int sa_wire_decode_queries_embed(const uint8_t* buf, const uint64_t* value_off, const uint32_t* value_len, int n, int dim,
                                  uint32_t schema_id, float* out_vec, uint64_t* text_off, uint32_t* text_len,
                                  uint8_t* status, int* n_ok);
+
+/* Batch decode of documents_embed values (the ingest side: `documents -> documents_embed -> vector table`,
+ * LAB2-Walkthrough.md:41-51; schema = document_id, chunk, embedding + Lab4's six metadata columns,
+ * terraform/lab4-pubsec-fraud-agents/main.tf:271-289).  status as above (0 decoded / 1 hand to the generic codec).
+ * For status-0 records: out_vec row = embedding; id_* / chunk_* = the UTF-8 text inside buf (len 0xFFFFFFFF = null);
+ * meta_* = the bytes of the six metadata fields (validated, decoded lazily by the caller). */
+int sa_wire_decode_documents_embed(const uint8_t* buf, const uint64_t* value_off, const uint32_t* value_len, int n, int dim,
+                                   uint32_t schema_id, float* out_vec, uint64_t* id_off, uint32_t* id_len,
+                                   uint64_t* chunk_off, uint32_t* chunk_len, uint64_t* meta_off, uint32_t* meta_len,
+                                   uint8_t* status, int* n_ok);
 
 /* Batch encode of search_results records, already framed for the file log (null key, timestamp ts_ms), ready to be
  * appended with one write.  Record i: query text = text_buf[text_off[i] .. +text_len[i]) (text_len 0xFFFFFFFF = null),

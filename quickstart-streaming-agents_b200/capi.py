@@ -34,7 +34,7 @@ EXPORTS = (
     "sa_get_info", "sa_scan_profile", "sa_debug_tile_dots", "sa_debug_plan", "sa_debug_float_keys", "sa_debug_bf16_round",
     "sa_debug_merge_keys", "sa_debug_list_insert", "sa_host_alloc", "sa_host_free",
     # include/sa_wire.h
-    "sa_wire_split_log", "sa_wire_decode_queries_embed", "sa_wire_encode_search_results", "sa_wire_encode_queries_embed",
+    "sa_wire_split_log", "sa_wire_decode_queries_embed", "sa_wire_decode_documents_embed", "sa_wire_encode_search_results", "sa_wire_encode_queries_embed",
 )
 
 
@@ -109,6 +109,7 @@ def load() -> C.CDLL:
         "sa_debug_list_insert": (i32, [vp, vp, i32, i32, vp, vp, vp, vp]),
         "sa_wire_split_log": (i32, [vp, u64, i32, vp, vp, vp, vp, vp]),
         "sa_wire_decode_queries_embed": (i32, [vp, vp, vp, i32, i32, C.c_uint32, vp, vp, vp, vp, C.POINTER(i32)]),
+        "sa_wire_decode_documents_embed": (i32, [vp, vp, vp, i32, i32, C.c_uint32, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(i32)]),
         "sa_wire_encode_search_results": (i32, [i32, i32, i32, C.c_uint32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i64,
                                                 vp, u64, vp, C.POINTER(u64)]),
         "sa_wire_encode_queries_embed": (i32, [i32, i32, C.c_uint32, vp, vp, vp, vp, i64, vp, u64, vp, C.POINTER(u64)]),

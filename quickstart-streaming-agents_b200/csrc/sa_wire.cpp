@@ -154,6 +154,135 @@ int sa_wire_decode_queries_embed(const uint8_t* buf, const uint64_t* value_off, 
   return SA_OK;
 }
 
+namespace {
+// Skip one Avro value of the shapes the metadata columns have; false = malformed / truncated.
+inline bool skip_nullable_string(const uint8_t*& p, const uint8_t* end) {
+  int64_t br;
+  if (!read_long(p, end, &br, &p)) return false;
+  if (br == 0) return true;
+  if (br != 1) return false;
+  int64_t n;
+  if (!read_long(p, end, &n, &p) || n < 0 || n > end - p) return false;
+  p += n;
+  return true;
+}
+inline bool skip_nullable_string_array(const uint8_t*& p, const uint8_t* end) {
+  int64_t br;
+  if (!read_long(p, end, &br, &p)) return false;
+  if (br == 0) return true;
+  if (br != 1) return false;
+  for (;;) {
+    int64_t cnt;
+    if (!read_long(p, end, &cnt, &p)) return false;
+    if (cnt == 0) return true;
+    if (cnt < 0) {
+      int64_t bytes;
+      if (!read_long(p, end, &bytes, &p)) return false;
+      cnt = -cnt;
+    }
+    for (int64_t i = 0; i < cnt; ++i)
+      if (!skip_nullable_string(p, end)) return false;
+  }
+}
+inline bool skip_nullable_int(const uint8_t*& p, const uint8_t* end) {
+  int64_t br, v;
+  if (!read_long(p, end, &br, &p)) return false;
+  if (br == 0) return true;
+  return br == 1 && read_long(p, end, &v, &p);
+}
+}  // namespace
+
+int sa_wire_decode_documents_embed(const uint8_t* buf, const uint64_t* value_off, const uint32_t* value_len, int n, int dim,
+                                   uint32_t schema_id, float* out_vec, uint64_t* id_off, uint32_t* id_len,
+                                   uint64_t* chunk_off, uint32_t* chunk_len, uint64_t* meta_off, uint32_t* meta_len,
+                                   uint8_t* status, int* n_ok) {
+  if (!buf || !value_off || !value_len || !out_vec || !id_off || !id_len || !chunk_off || !chunk_len || !meta_off ||
+      !meta_len || !status || n < 0 || dim <= 0)
+    return sa_internal_fail(SA_ERR_ARG, "sa_wire_decode_documents_embed: bad argument");
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    float* dst = out_vec + static_cast<size_t>(i) * dim;
+    status[i] = 1;
+    id_off[i] = chunk_off[i] = meta_off[i] = 0;
+    id_len[i] = chunk_len[i] = kNullLen;
+    meta_len[i] = 0;
+    bool good = false;
+    do {
+      const uint32_t vl = value_len[i];
+      if (vl == kNullLen || vl < 5) break;
+      const uint8_t* p = buf + value_off[i];
+      const uint8_t* end = p + vl;
+      if (p[0] != 0) break;
+      const uint32_t sid = (static_cast<uint32_t>(p[1]) << 24) | (static_cast<uint32_t>(p[2]) << 16) |
+                           (static_cast<uint32_t>(p[3]) << 8) | p[4];
+      if (sid != schema_id) break;
+      p += 5;
+      // document_id, chunk: ["null","string"] (either may be null)
+      uint64_t so[2];
+      uint32_t sl[2];
+      bool strings_ok = true;
+      for (int f = 0; f < 2; ++f) {
+        int64_t br;
+        if (!read_long(p, end, &br, &p) || (br != 0 && br != 1)) {
+          strings_ok = false;
+          break;
+        }
+        so[f] = 0;
+        sl[f] = kNullLen;
+        if (br == 1) {
+          int64_t tl;
+          if (!read_long(p, end, &tl, &p) || tl < 0 || tl > end - p) {
+            strings_ok = false;
+            break;
+          }
+          so[f] = static_cast<uint64_t>(p - buf);
+          sl[f] = static_cast<uint32_t>(tl);
+          p += tl;
+        }
+      }
+      if (!strings_ok) break;
+      // embedding: one block of exactly dim non-null finite floats
+      if (p >= end || *p++ != 2) break;
+      int64_t cnt;
+      if (!read_long(p, end, &cnt, &p) || cnt != dim) break;
+      if (end - p < static_cast<int64_t>(dim) * 5 + 1) break;
+      bool items_ok = true;
+      for (int j = 0; j < dim; ++j) {
+        float f;
+        memcpy(&f, p + 1, 4);
+        if (p[0] != 2 || !std::isfinite(f)) {
+          items_ok = false;
+          break;
+        }
+        dst[j] = f;
+        p += 5;
+      }
+      if (!items_ok || *p++ != 0) break;
+      // metadata columns (terraform/lab4-pubsec-fraud-agents/main.tf:271-289): validated here, decoded lazily by the host
+      const uint8_t* m0 = p;
+      if (!skip_nullable_string(p, end) || !skip_nullable_string(p, end) || !skip_nullable_string(p, end) ||
+          !skip_nullable_string_array(p, end) || !skip_nullable_string_array(p, end) || !skip_nullable_int(p, end))
+        break;
+      if (p != end) break;
+      id_off[i] = so[0];
+      id_len[i] = sl[0];
+      chunk_off[i] = so[1];
+      chunk_len[i] = sl[1];
+      meta_off[i] = static_cast<uint64_t>(m0 - buf);
+      meta_len[i] = static_cast<uint32_t>(end - m0);
+      good = true;
+    } while (false);
+    if (good) {
+      status[i] = 0;
+      ++ok;
+    } else {
+      memset(dst, 0, sizeof(float) * dim);
+    }
+  }
+  if (n_ok) *n_ok = ok;
+  return SA_OK;
+}
+
 int sa_wire_encode_search_results(int n, int k, int n_out, uint32_t schema_id, const uint8_t* text_buf,
                                   const uint64_t* text_off, const uint32_t* text_len, const float* score,
                                   const int64_t* row, const uint8_t* doc_arena, const uint64_t* doc_off,

@@ -61,6 +61,27 @@ class ByteArena:
         self.n += 1
         self.off[self.n] = need
 
+    def extend(self, items: list[bytes]) -> None:
+        """Append many values with one copy (what the ingest path uses: a batch at a time)."""
+        if not items:
+            return
+        blob = b"".join(items)
+        need = self.used + len(blob)
+        if need > self.data.size:
+            grown = np.zeros(max(need, 2 * self.data.size), dtype=np.uint8)
+            grown[:self.used] = self.data[:self.used]
+            self.data = grown
+        m = len(items)
+        if self.n + m + 1 > self.off.size:
+            grown = np.zeros(max(self.n + m + 1, 2 * self.off.size), dtype=np.uint64)
+            grown[:self.n + 1] = self.off[:self.n + 1]
+            self.off = grown
+        self.data[self.used:need] = np.frombuffer(blob, dtype=np.uint8)
+        lens = np.fromiter(map(len, items), dtype=np.uint64, count=m)
+        self.off[self.n + 1:self.n + m + 1] = np.uint64(self.used) + np.cumsum(lens)
+        self.used = need
+        self.n += m
+
     def clear(self) -> None:
         self.n = 0
         self.used = 0
@@ -117,15 +138,22 @@ class VectorTable:
         keep = [i for i, d in enumerate(document_ids) if d is None or last[d] == i]
         if stale:
             self.index.delete_rows(stale)
-        first = self.index.append(embeddings[keep])
+        first = self.index.append(embeddings if len(keep) == n else embeddings[keep])
         assert first == len(self.document_id), "side table and index out of step"
-        for j, i in enumerate(keep):
-            self.document_id.append(document_ids[i])
-            self.chunk.append(chunks[i])
-            self.metadata.append(metadata[i])
-            self._push_avro(document_ids[i], chunks[i])
-            if document_ids[i] is not None:
-                self._row_of[document_ids[i]] = first + j
+        ids = [document_ids[i] for i in keep]
+        chs = [chunks[i] for i in keep]
+        self.document_id.extend(ids)
+        self.chunk.extend(chs)
+        self.metadata.extend(metadata[i] for i in keep)
+        enc_d = [_avro_nullable_string(d) for d in ids]
+        enc_c = [_avro_nullable_string(c) for c in chs]
+        self.avro_document_id.extend(enc_d)
+        self.avro_chunk.extend(enc_c)
+        self.arena_document_id.extend(enc_d)
+        self.arena_chunk.extend(enc_c)
+        for j, d in enumerate(ids):
+            if d is not None:
+                self._row_of[d] = first + j
 
     def load_columns(self, document_ids, chunks, metadata=None) -> None:
         """Attach the non-vector columns for rows whose vectors are ALREADY in the index (bulk load of a pre-built

@@ -194,6 +194,71 @@ class Lab2Pipeline:
         return len(msgs)
 
     def stage_sink(self) -> int:
+        """documents_embed -> vector table.  Batch path: one read of the partition log, native split + decode of ids, chunks
+        and embeddings (sa_wire_decode_documents_embed; the six metadata columns are validated natively and decoded only
+        when they are not all null), one upsert per batch; records in an unusual shape go through the generic codec."""
+        c = self.consumers["documents_embed"]
+        if self._wire is not None and hasattr(c, "consume_raw"):
+            return self._stage_sink_native()
+        return self._stage_sink_generic()
+
+    def _stage_sink_native(self) -> int:
+        c = self.consumers["documents_embed"]
+        lib, dim = self._wire, self.table.index.dim
+        if not hasattr(self, "_meta_codec"):
+            fields = [f for f in schemas.DOCUMENTS_EMBED_VALUE["fields"] if f["name"] in schemas.METADATA_COLUMNS]
+            self._meta_codec = avro.CompiledSchema({"type": "record", "name": "documents_embed_metadata", "fields": fields})
+            self._null_meta = {col: None for col in schemas.METADATA_COLUMNS}
+        total = 0
+        while True:
+            raw = c.consume_raw(self.max_batch)
+            if raw is None:
+                break
+            topic, part, first, n, data = raw
+            total += n
+            voff, vlen = np.empty(n, np.uint64), np.empty(n, np.uint32)
+            if lib.sa_wire_split_log(data, len(data), n, voff.ctypes.data, vlen.ctypes.data, None, None, None):
+                raise avro.AvroError("corrupt log slice: " + lib.sa_last_error().decode())
+            vecs = np.empty((n, dim), np.float32)
+            io, co, mo = (np.empty(n, np.uint64) for _ in range(3))
+            il, cl, ml = (np.empty(n, np.uint32) for _ in range(3))
+            status = np.empty(n, np.uint8)
+            n_ok = C.c_int()
+            if lib.sa_wire_decode_documents_embed(data, voff.ctypes.data, vlen.ctypes.data, n, dim,
+                                                  self.codec.schema_id("documents_embed"), vecs.ctypes.data, io.ctypes.data,
+                                                  il.ctypes.data, co.ctypes.data, cl.ctypes.data, mo.ctypes.data,
+                                                  ml.ctypes.data, status.ctypes.data, C.byref(n_ok)):
+                raise avro.AvroError(lib.sa_last_error().decode())
+            ids, chunks, metas, keep = [], [], [], []
+            io_l, il_l, co_l, cl_l, mo_l, ml_l, st_l = (x.tolist() for x in (io, il, co, cl, mo, ml, status))
+            for i in range(n):
+                if st_l[i] == 0:
+                    ids.append(None if il_l[i] == 0xFFFFFFFF else data[io_l[i]:io_l[i] + il_l[i]].decode("utf-8"))
+                    chunks.append(None if cl_l[i] == 0xFFFFFFFF else data[co_l[i]:co_l[i] + cl_l[i]].decode("utf-8"))
+                    mb = data[mo_l[i]:mo_l[i] + ml_l[i]]
+                    metas.append(dict(self._null_meta) if mb == b"\x00\x00\x00\x00\x00\x00" else self._meta_codec.decode(mb))
+                    keep.append(i)
+                    continue
+                value = None if vlen[i] == 0xFFFFFFFF else data[int(voff[i]):int(voff[i]) + int(vlen[i])]
+                m = Message(topic, part, first + i, None, value, 0)
+                got = self._decode_all("documents_embed", [m])
+                if not got or not self._check_vec("documents_embed", m, got[0][1].get("embedding")):
+                    continue
+                r = got[0][1]
+                vecs[i] = r["embedding"]
+                ids.append(r.get("document_id"))
+                chunks.append(r.get("chunk"))
+                metas.append({col: r.get(col) for col in schemas.METADATA_COLUMNS})
+                keep.append(i)
+            if ids:
+                self.table.upsert_many(ids, chunks, vecs if len(keep) == n else vecs[keep], metas)
+                self.stats["documents"] += len(ids)
+                self._sink_dirty = True
+            self.producer.flush()     # quarantined records, if any
+            c.commit_upto(topic, part, first + n)   # informational only: the sink's start position comes from the table
+        return total
+
+    def _stage_sink_generic(self) -> int:
         c, msgs, recs = self._drain("documents_embed")
         ids, chunks, vecs, metas = [], [], [], []
         for m, r in recs:
