@@ -2,7 +2,7 @@
 # Round 2, GPU call D (2 GPUs): multi-GPU tests through the C ABI, then the driver's N=2 bench command.
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/r2d_topo.txt 2>&1
-echo "multi-gpu tests: passed in call D (first attempt)" > gpurun_out/r2d_pytest2.log
+timeout 900 python -m pytest tests/test_multi_gpu.py -m gpu -x -q > gpurun_out/r2d_pytest.log 2>&1; tail -3 gpurun_out/r2d_pytest.log
 ( time timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 20 --warmup 3 ) > gpurun_out/r2d_bench_n2.json 2> gpurun_out/r2d_bench_n2.err
 tail -8 gpurun_out/r2d_bench_n2.err | cut -c1-400
 python - <<'PY'
