@@ -24,6 +24,10 @@ config 4's batch and config 5's shard shape with streaming epochs), each with it
 
 `--impl reference` times the CPU arm instead: the numpy brute-force oracle with all host
 threads on a bounded sample of the same workload.  It never touches the GPU engine.
+
+Use of `oracle/` here: (i) the canonical DATA recipe (`synth_rows` / `synth_queries`) in the worker
+pool, (ii) the recall / parity CHECKS after the timed regions, (iii) the CPU legs (`cpu_baseline`, `--impl reference`).
+Nothing under `oracle/` is on any timed GPU path, and the engine never imports it.
 """
 from __future__ import annotations
 
@@ -85,6 +89,11 @@ def parse_args():
     ap.add_argument("--data", default="numpy", choices=["numpy", "philox"],
                     help="philox: device generator for chunks >= 1 (quick profiling runs only; chunk 0 stays canonical)")
     return ap.parse_args()
+
+
+def bits_to_f32(bits):
+    """bf16 bit patterns (uint16) -> the float32 values they denote."""
+    return (np.ascontiguousarray(bits, dtype=np.uint16).astype(np.uint32) << 16).view(np.float32)
 
 
 def workload_name(rows, dim, batch, k):
@@ -462,8 +471,7 @@ class Workload:
         torch = env["torch"]
         self.q_bf16 = torch.from_numpy(q_bits.view(np.int16)).view(torch.bfloat16).cuda()
         from qsa_b200.engine import pinned_array
-        from oracle import bruteforce as bf
-        qf = bf.bf16_bits_to_f32(q_bits)
+        qf = bits_to_f32(q_bits)
         self.q_host = [pinned_array((B, dim), np.float32) for _ in range(2)]
         for h in self.q_host:
             h[:] = qf
@@ -694,8 +702,7 @@ def pipeline_e2e(env, index_like, n_total, dim, B, k, q_bits, est_batch_s, min_t
         # ---- the input topic: n_batches x B records, encoded and framed natively, one append per batch
         n_batches = max(4, int(math.ceil(min_timed_s / max(est_batch_s, 1e-6))))
         n_batches = min(n_batches, 256)
-        from oracle import bruteforce as bf
-        vec = np.ascontiguousarray(bf.bf16_bits_to_f32(q_bits))
+        vec = np.ascontiguousarray(bits_to_f32(q_bits))
         texts = [f"question {i}".encode() for i in range(B)]
         tbuf = b"".join(texts)
         tlen = np.array([len(t) for t in texts], np.uint32)

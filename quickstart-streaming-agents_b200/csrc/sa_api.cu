@@ -99,6 +99,7 @@ struct DeviceGuard {
   if (_dg.rc != cudaSuccess) return fail(SA_ERR_CUDA, "cudaSetDevice(%d) failed: %s", (dev), cudaGetErrorString(_dg.rc))
 
 constexpr int kMaxLaunches = 16;
+constexpr int kDefaultWaitHintNs = 0;  // set from tools/gpu_sweep.py --opt wait_hint_ns=... (profiles/)
 constexpr int kDefaultPresample = 0;   // set from tools/gpu_worstcase.py / gpu_sweep.py (profiles/)
 constexpr int kTimingRing = 16;
 constexpr int kHostSlots = SA_HOST_SLOTS;
@@ -173,6 +174,7 @@ struct sa_engine {
   int opt_pace_max = -1;   // -1 = auto (8 x gain)
   int opt_unit_map = 0;
   int opt_list_len = 0;    // 0 = auto (16 when k <= 12, else 32)
+  int opt_wait_hint_ns = -1;  // suspend-time hint of the epilogue's mbarrier waits (-1 = auto, 0 = plain polling)
   int opt_presample = -1;  // tile stride of the sampling pre-pass that seeds the shared thresholds (-1 = auto, 0 = off)
   int opt_force_fix = 0;   // test hook: every (query, lane) goes through the exact fallback scan
   int64_t last_fix_entries = -1;  // option "count_fix": work-queue length of the last search (costs a host sync)
@@ -396,6 +398,7 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
     sp.part_drop = e->part_drop;
     sp.corpus_evict_first = (lp.nqb == 1) ? 1 : 0;  // a tile nobody else will ask for: stream it through L2
     sp.tile_stride = 1;
+    sp.wait_hint_ns = e->opt_wait_hint_ns >= 0 ? e->opt_wait_hint_ns : kDefaultWaitHintNs;
     sp.lane_progress = nullptr;
     sp.max_drift = e->opt_max_drift >= 0 ? e->opt_max_drift : 1;
     sp.pace_gain = 0;
@@ -1336,6 +1339,11 @@ int sa_set_option(sa_engine* e, const char* name, int64_t value) {
   if (!strcmp(name, "max_launch_qblocks")) {
     if (value < 0) return fail(SA_ERR_ARG, "max_launch_qblocks must be >= 0");
     e->opt_max_launch_qblocks = static_cast<int>(value);
+    return SA_OK;
+  }
+  if (!strcmp(name, "wait_hint_ns")) {
+    if (value < -1 || value > 1000000) return fail(SA_ERR_ARG, "wait_hint_ns must be in [-1, 1000000]");
+    e->opt_wait_hint_ns = static_cast<int>(value);
     return SA_OK;
   }
   if (!strcmp(name, "presample")) {

@@ -76,6 +76,7 @@ struct ScanParams {
   float* part_drop;       // [gridDim.x][128]  upper bound on the approximate score of the lane's rows not in the list
   int corpus_evict_first; // 1: corpus tiles are read by a single query block -> stream them through L2
   int tile_stride;        // 1: walk every tile; S > 1: the sampling pre-pass walks tiles 0, S, 2S, ... only
+  int wait_hint_ns;       // suspend-time hint of the epilogue's mbarrier waits (0 = plain polling)
   int* lane_progress;     // [tl_count][nqb] tiles whose loads each unit has issued (zero at launch), or nullptr
   int unit_map;           // 0: unit = tl*nqb + qb (lane-mates adjacent), 1: unit = qb*TL + tl (lane-mates TL apart)
   int max_drift;          // lead (in tiles) over the slowest lane-mate that is not paced
@@ -532,7 +533,7 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       const uint32_t aph = (it >> 1) & 1u;
       long long c0 = 0;
       if constexpr (kProf) c0 = clock64();
-      mbar_wait(tfull_bar(a), aph);
+      mbar_wait(tfull_bar(a), aph, static_cast<uint32_t>(p.wait_hint_ns));
       tc_fence_after();
       long long c1 = 0;
       if constexpr (kProf) c1 = clock64();
