@@ -460,6 +460,35 @@ def _all_reduce_max_list(vals, dist, torch):
     return t.tolist()
 
 
+def settle_and_estimate(step, sync, barrier, sampler, world, allmax, steps, min_timed_s, preheat_max, settle_s=1.5):
+    """Bring the GPU to its sustained state and size a step.  Returns (batches per step, preheat seconds, preheat batches,
+    seconds per batch).
+      1. one-time costs first (NCCL connection set-up, first-use allocations): they must not reach any estimate -- a first
+         version let them in, took 0.3 s for a batch, and timed a 0.06 s region at boost clocks;
+      2. preheat (untimed) until the SM clock is stable UNDER LOAD: a 1 kW part boosts for the first second and then
+         settles at its power cap; the roofline denominator (cuBLAS, 4 s back to back) is a settled number;
+      3. seconds per batch from a short settled burst; a step = as many batches as make the timed region >= min_timed_s."""
+    for _ in range(3):
+        step()
+    barrier()
+    t_ph0 = time.perf_counter()
+
+    def stop_flags():
+        el = time.perf_counter() - t_ph0
+        return (el >= settle_s and sampler.stable()), el >= preheat_max
+    n_ph, ph_s = collective_preheat(step, sync, stop_flags, world, allmax)
+    barrier()
+    t_e0 = time.perf_counter()
+    for _ in range(8):
+        step()
+    sync()
+    est = (time.perf_counter() - t_e0) / 8
+    if world > 1:
+        est = allmax([est])[0]
+    inner = max(1, int(math.ceil(min_timed_s / max(steps * est, 1e-9))))
+    return inner, ph_s, n_ph, est
+
+
 class Workload:
     """One (corpus shard, batch, k) measurement on this rank's engine: device-resident loop, host-buffer e2e loops,
     scan-kernel event times, recall against the oracle."""
@@ -520,28 +549,8 @@ class Workload:
         a, env = self.a, self.env
         torch = env["torch"]
         world = env["world"]
-        # ---- one-time costs first (NCCL connection set-up, first-use allocations): they must not reach any estimate
-        for _ in range(3):
-            self.step_device()
-        env["barrier"]()
-        # ---- preheat (untimed) until the SM clock is stable UNDER LOAD: a 1 kW part boosts for the first second and then
-        # settles at its power cap; the roofline denominator (cuBLAS, 4 s back to back) is a settled number
-        t_ph0 = time.perf_counter()
-
-        def stop_flags():
-            el = time.perf_counter() - t_ph0
-            return (el >= 1.5 and sampler.stable()), el >= preheat_max
-        n_ph, ph_s = collective_preheat(self.step_device, torch.cuda.synchronize, stop_flags, world, env["allmax"])
-        # seconds per batch from a short, settled burst (the preheat total would include the boost phase)
-        env["barrier"]()
-        t_e0 = time.perf_counter()
-        for _ in range(8):
-            self.step_device()
-        torch.cuda.synchronize()
-        est = (time.perf_counter() - t_e0) / 8
-        if world > 1:
-            est = env["allmax"]([est])[0]
-        inner = max(1, int(math.ceil(min_timed_s / max(steps * est, 1e-9))))
+        inner, ph_s, n_ph, est = settle_and_estimate(self.step_device, torch.cuda.synchronize, env["barrier"], sampler, world,
+                                                     env["allmax"], steps, min_timed_s, preheat_max)
         # ---- warm-up steps
         for _ in range(warmup):
             out = self.step_device()

@@ -76,6 +76,26 @@ def test_preheat_single_rank_stops_on_stable_or_timeout():
     assert n % 4 == 0 and n >= 8 and secs >= 0.05                         # never stable: runs into the time limit
 
 
+def test_step_size_estimate_ignores_one_time_costs():
+    """The batches-per-step estimate must come from settled batches: a slow first call (NCCL connection set-up took 0.3 s
+    once and produced a 0.06 s 'timed region' at N = 8) may not leak into it."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    class Sampler:
+        def stable(self):
+            return True
+    calls = [0]
+
+    def step():
+        calls[0] += 1
+        time.sleep(0.25 if calls[0] == 1 else 0.002)
+    inner, ph_s, n_ph, est = bench.settle_and_estimate(step, lambda: None, lambda: None, Sampler(), 1, None, steps=10,
+                                                       min_timed_s=0.5, preheat_max=0.4, settle_s=0.1)
+    assert est < 0.01 and 15 <= inner <= 30            # ~2.2 ms per batch -> ~23 batches per step, not 1
+    assert n_ph >= 4 and ph_s < 0.5
+
+
 def test_host_data_pool_generates_canonical_chunks_and_the_parallel_oracle_equals_the_definition():
     """bench.py's worker pool: (i) what it writes into the shared mapping IS oracle.synth_rows chunk by chunk, also when a
     shard boundary cuts a chunk; (ii) its parallel oracle (per-piece fp32 prefilter + float64 re-scoring) returns exactly
