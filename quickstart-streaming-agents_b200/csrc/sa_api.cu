@@ -403,9 +403,10 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
     sp.max_drift = e->opt_max_drift >= 0 ? e->opt_max_drift : 1;
     sp.pace_gain = 0;
     sp.unit_map = e->opt_unit_map;
-    // drift-control defaults from the sweeps in tools/gpu_l2exp.sh (DRAM bytes vs time): pairs 16 cycles per tile of
-    // lead beyond 1 tile, single CTAs 32
-    const int gain = e->opt_pace_gain >= 0 ? e->opt_pace_gain : (lp.cg == 2 ? 16 : 32);
+    // drift-control defaults: round 1 tuned them on DRAM bytes (pairs 16 cycles per tile of lead beyond 1 tile); re-tuned
+    // on scan time after the epilogue rewrite (profiles/r02_sweep_drift_control.json, B = 1024: no pacing 28.8 ms,
+    // gain 16 -> 26.2, 32 -> 25.9, 64 -> 25.75; max_drift 0 / 2 no better than 1)
+    const int gain = e->opt_pace_gain >= 0 ? e->opt_pace_gain : (lp.cg == 2 ? 64 : 32);
     sp.pace_max = e->opt_pace_max >= 0 ? e->opt_pace_max : 8 * gain;
     if (lp.nqb > 1 && gain > 0) {
       sp.lane_progress = e->lane_progress + li * e->num_sms;  // this launch's slice (zero: see sa_engine)
@@ -607,7 +608,7 @@ int sa_engine_create(sa_engine** out, int device, int dim, int64_t capacity_rows
   if (prop.major != 10)
     return fail(SA_ERR_DEVICE, "device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major,
                 prop.minor);
-  SA_CUDA(cudaSetDevice(device));
+  SA_ON_DEVICE(device);
   if (!get_encode_fn()) return fail(SA_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
 
   sa_engine* e = new sa_engine();
@@ -683,7 +684,7 @@ int sa_engine_create(sa_engine** out, int device, int dim, int64_t capacity_rows
 
 void sa_engine_destroy(sa_engine* e) {
   if (!e) return;
-  cudaSetDevice(e->device);
+  DeviceGuard dg(e->device);  // the caller's current device is restored on return
   cudaDeviceSynchronize();
   cudaFree(e->part_score);
   cudaFree(e->part_idx);
