@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """ncu -i <rep> --page raw --csv  ->  profiles/<name>.summary.csv (metric, unit, value), keeping the metrics that matter
-for this kernel: DRAM bytes / throughput, L2 hit rate and traffic, tensor-pipe activity, issue stalls, launch shape.
+for this kernel: DRAM bytes / throughput, L2 hit rate, L2->SM bytes (xbar2l1tex, the TMA loads), tensor-pipe activity, issue stalls, launch shape.
 Usage (here, no GPU needed):  python tools/ncu_summary.py gpurun_out/x.ncu-rep profiles/r02_x.summary.csv"""
 import csv
 import re
@@ -11,7 +11,9 @@ KEEP = re.compile(r"^(dram__bytes|dram__cycles_elapsed|dram__throughput|gpu__dra
                   r"l1tex__data_pipe_lsu_wavefronts(_mem_shared)?\.sum$|launch__|lts__t_sector_hit_rate|lts__t_bytes|"
                   r"lts__t_sectors_srcunit_tex_op_read|lts__throughput|lts__cycles_elapsed|sm__cycles_(active|elapsed)|"
                   r"sm__inst_executed_pipe_tensor|sm__pipe_tensor|sm__throughput|sm__warps_active|smsp__average_warp|"
-                  r"smsp__inst_executed\.sum|smsp__cycles_active\.avg$)")
+                  r"smsp__inst_executed\.sum|smsp__cycles_active\.avg$|"
+                  r"l1tex__m_xbar2l1tex_read_bytes(_mem_global_op_tma_ld)?\.sum(\.per_second)?$|lts__t_sectors_srcunit_tex\.sum$|"
+                  r"lts__t_sectors\.sum$)")
 
 
 def main():
