@@ -159,6 +159,8 @@ int sa_timing_mean(sa_engine* e, int n, float* scan_ms_mean, float* total_ms_mea
  * once): "max_drift" = unpaced lead in tiles (-1 auto), "pace_gain" = delay cycles per K-slice per extra tile
  * of lead (-1 auto, 0 off), "pace_max" = cap of that delay (-1 auto);
  * "share_thresholds" = 1 | 0 (tile lanes exchange per-query top-k thresholds; default 1), "list_len" = 0 (auto) | 16 | 32,
+ * "window_bound" = 1 | 0 (with >= 16 tile lanes, a lane also bounds its threshold by the (list_len/2)-th largest of 16
+ * lanes' second-best scores -- list_len rows in all -- which is far tighter while the lists are young; default 1),
  * "presample" = S (a pre-pass over every S-th tile seeds those thresholds, so the order of the rows cannot hurt; 0 off, -1 auto),
  * "unit_map" = 0 | 1 (CTA -> (query block, tile lane) mapping), "record_times" = 0 | 1 (per-CTA timestamps),
  * "profile" = 0 | 1 (run the scan's profiling build: per-CTA role wait/busy cycle counters, see sa_scan_profile),
@@ -193,6 +195,10 @@ int sa_debug_bf16_round(const float* x, int n, uint16_t* bits, float* back);
 int sa_debug_merge_keys(const float* score, const int32_t* row, int n, uint64_t* key, int32_t* row_back);
 int sa_debug_list_insert(const float* score, const int32_t* row, int n, int list_len, const float* floor_after,
                          float* out_score, int32_t* out_row, float* out_drop);
+/* The window bound of the scan's epilogue: for each of n_windows groups of 16 keys (16 tile lanes' second-best scores of
+ * one query as order-preserving keys, 0 = not published yet) the (list_len/2)-th largest key (0 = no bound yet);
+ * out_sorted (optional) receives each window sorted descending by the kernel's 16-input network. */
+int sa_debug_window_bound(const uint32_t* keys, int n_windows, int list_len, uint32_t* out_bound, uint32_t* out_sorted);
 
 /* Pinned host memory for callers that want truly asynchronous staging. */
 int sa_host_alloc(void** out, uint64_t bytes);

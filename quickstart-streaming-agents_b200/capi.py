@@ -32,7 +32,7 @@ EXPORTS = (
     "sa_sharded_search_host_wait", "sa_gather_merge", "sa_gather_merge_submit", "sa_gather_merge_wait",
     "sa_last_timing", "sa_timing_mean", "sa_set_option",
     "sa_get_info", "sa_scan_profile", "sa_debug_tile_dots", "sa_debug_plan", "sa_debug_float_keys", "sa_debug_bf16_round",
-    "sa_debug_merge_keys", "sa_debug_list_insert", "sa_host_alloc", "sa_host_free",
+    "sa_debug_merge_keys", "sa_debug_list_insert", "sa_debug_window_bound", "sa_host_alloc", "sa_host_free",
     # include/sa_wire.h
     "sa_wire_split_log", "sa_wire_decode_queries_embed", "sa_wire_decode_documents_embed", "sa_wire_encode_search_results", "sa_wire_encode_queries_embed",
 )
@@ -107,6 +107,7 @@ def load() -> C.CDLL:
         "sa_debug_bf16_round": (i32, [vp, i32, vp, vp]),
         "sa_debug_merge_keys": (i32, [vp, vp, i32, vp, vp]),
         "sa_debug_list_insert": (i32, [vp, vp, i32, i32, vp, vp, vp, vp]),
+        "sa_debug_window_bound": (i32, [vp, i32, i32, vp, vp]),
         "sa_wire_split_log": (i32, [vp, u64, i32, vp, vp, vp, vp, vp]),
         "sa_wire_decode_queries_embed": (i32, [vp, vp, vp, i32, i32, C.c_uint32, vp, vp, vp, vp, C.POINTER(i32)]),
         "sa_wire_decode_documents_embed": (i32, [vp, vp, vp, i32, i32, C.c_uint32, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(i32)]),

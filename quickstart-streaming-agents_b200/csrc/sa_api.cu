@@ -163,8 +163,10 @@ struct sa_engine {
   unsigned* thr_shared = nullptr;
   int thr_n = 0;
   int* lane_progress = nullptr;
+  unsigned* lane2 = nullptr;  // [kMaxLaunches][num_sms * 128] the lanes' second-best scores (window bound); zero like the above
   bool scratch_dirty = false;  // a search failed between its first launch and its last: re-zero before the next one
   int opt_share_thresholds = 1;
+  int opt_window_bound = 1;
 
   // options
   int opt_cta_group = 0;
@@ -337,6 +339,7 @@ float scan_eps_rel(int dim) { return (1.0625f * dim + 16.0f) * 1.1920929e-07f; }
 int zero_scan_scratch(sa_engine* e, cudaStream_t st) {
   SA_CUDA(cudaMemsetAsync(e->thr_shared, 0, sizeof(unsigned) * e->thr_n, st));
   SA_CUDA(cudaMemsetAsync(e->lane_progress, 0, sizeof(int) * kMaxLaunches * e->num_sms, st));
+  SA_CUDA(cudaMemsetAsync(e->lane2, 0, sizeof(unsigned) * kMaxLaunches * e->num_sms * 128, st));
   SA_CUDA(cudaMemsetAsync(e->fix_counters, 0, sizeof(int) * 2, st));
   return SA_OK;
 }
@@ -416,6 +419,9 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
     // a pre-pass only pays when every lane still has a long walk ahead of it after the sample
     const bool do_presample = presample > 1 && e->opt_share_thresholds && num_tiles >= 4 * presample * lp.tl;
     sp.thr_shared = (e->opt_share_thresholds && (lp.tl > 1 || do_presample)) ? e->thr_shared + lp.q0 : nullptr;
+    // window bound: lp.tl * lp.nqb * 128 * lp.cg <= num_sms * 128 slots, this launch's slice of the table
+    sp.lane2 = (sp.thr_shared != nullptr && e->opt_window_bound && lp.tl >= sa::kWin)
+                   ? e->lane2 + static_cast<size_t>(li) * e->num_sms * 128 : nullptr;
     sp.dbg_dots = nullptr;
     sp.dbg_tile = -1;
     sp.dbg_times = e->opt_record_times ? e->dbg_times : nullptr;
@@ -434,6 +440,7 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
       pp.tile_stride = presample;
       pp.lane_progress = nullptr;  // no pacing: the pre-pass is short
       pp.pace_gain = 0;
+      pp.lane2 = nullptr;
       pp.prof = e->prof;
       rc = launch_scan_dispatch(lp.cg, kl, sa::kModeProd, tq, e->tmap_c[lp.cg - 1], pp, grid, st);
       if (rc) return rc;
@@ -525,6 +532,8 @@ int do_search(sa_engine* e, const uint16_t* q_bf16, int nq, int k, float* out_sc
     fp.zero_a_n = std::min(e->thr_n, ((nq + 255) / 256) * 256);
     fp.zero_b = e->lane_progress;
     fp.zero_b_n = static_cast<int>(plan.size()) * e->num_sms;
+    fp.zero_c = e->lane2;
+    fp.zero_c_n = e->opt_window_bound ? static_cast<int>(plan.size()) * e->num_sms * 128 : 0;
     const size_t smem = static_cast<size_t>(e->dim) * sizeof(float);
     if (smem > 48 * 1024)
       SA_CUDA(cudaFuncSetAttribute(sa::sa_fixup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -663,6 +672,8 @@ int sa_engine_create(sa_engine** out, int device, int dim, int64_t capacity_rows
   SA_TRY(cudaMalloc(&e->lane_progress, sizeof(int) * kMaxLaunches * e->num_sms));
   SA_TRY(cudaMalloc(&e->thr_shared, sizeof(unsigned) * e->thr_n));
   SA_TRY(cudaMemset(e->lane_progress, 0, sizeof(int) * kMaxLaunches * e->num_sms));
+  SA_TRY(cudaMalloc(&e->lane2, sizeof(unsigned) * kMaxLaunches * e->num_sms * 128));
+  SA_TRY(cudaMemset(e->lane2, 0, sizeof(unsigned) * kMaxLaunches * e->num_sms * 128));
   SA_TRY(cudaMemset(e->thr_shared, 0, sizeof(unsigned) * e->thr_n));
   SA_TRY(cudaMemset(e->fix_counters, 0, 2 * sizeof(int)));
   SA_TRY(cudaMemset(e->fix_query, 0, static_cast<size_t>(max_batch) * sizeof(sa::FixQuery)));
@@ -713,6 +724,7 @@ void sa_engine_destroy(sa_engine* e) {
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   if (e->scratch_free) cudaEventDestroy(e->scratch_free);
   cudaFree(e->lane_progress);
+  cudaFree(e->lane2);
   cudaFree(e->thr_shared);
   cudaFree(e->dbg_times);
   for (int r = 0; r < kTimingRing; ++r) {
@@ -1368,6 +1380,10 @@ int sa_set_option(sa_engine* e, const char* name, int64_t value) {
     e->opt_share_thresholds = value ? 1 : 0;
     return SA_OK;
   }
+  if (!strcmp(name, "window_bound")) {
+    e->opt_window_bound = value ? 1 : 0;
+    return SA_OK;
+  }
   if (!strcmp(name, "list_len")) {
     if (value != 0 && value != 16 && value != 32) return fail(SA_ERR_ARG, "list_len must be 0, 16 or 32");
     e->opt_list_len = static_cast<int>(value);
@@ -1520,6 +1536,19 @@ int sa_debug_list_insert(const float* score, const int32_t* row, int n, int list
   if (list_len == 16) run_list<16>(score, row, n, floor_after, out_score, out_row, out_drop);
   else if (list_len == 32) run_list<32>(score, row, n, floor_after, out_score, out_row, out_drop);
   else return fail(SA_ERR_ARG, "list_len must be 16 or 32");
+  return SA_OK;
+}
+
+int sa_debug_window_bound(const uint32_t* keys, int n_windows, int list_len, uint32_t* out_bound, uint32_t* out_sorted) {
+  if (!keys || !out_bound || n_windows < 0) return fail(SA_ERR_ARG, "bad argument");
+  if (list_len != 16 && list_len != 32) return fail(SA_ERR_ARG, "list_len must be 16 or 32");
+  for (int w = 0; w < n_windows; ++w) {
+    unsigned x[sa::kWin];
+    for (int i = 0; i < sa::kWin; ++i) x[i] = keys[static_cast<size_t>(w) * sa::kWin + i];
+    out_bound[w] = list_len == 16 ? sa::window_bound<16>(x) : sa::window_bound<32>(x);
+    if (out_sorted)
+      for (int i = 0; i < sa::kWin; ++i) out_sorted[static_cast<size_t>(w) * sa::kWin + i] = x[i];
+  }
   return SA_OK;
 }
 

@@ -386,8 +386,10 @@ struct FixParams {
   long long row_offset;     // first global row of this shard
   unsigned* zero_a;         // scratch to re-zero for the next search (shared thresholds) ...
   int zero_a_n;
-  int* zero_b;              // ... and drift counters
+  int* zero_b;              // ... drift counters
   int zero_b_n;
+  unsigned* zero_c;         // ... and the lanes' second-best table (window bound)
+  int zero_c_n;
 };
 
 constexpr int kFixThreads = 256;
@@ -411,6 +413,7 @@ __device__ __forceinline__ void fix_finalize(const FixParams& p, int first, int 
   }
   for (int i = first; i < p.zero_a_n; i += stride) p.zero_a[i] = 0u;
   for (int i = first; i < p.zero_b_n; i += stride) p.zero_b[i] = 0;
+  for (int i = first; i < p.zero_c_n; i += stride) p.zero_c[i] = 0u;
 }
 
 // Sorted insertion of (c, r) into a (cosine desc, row asc) list of k slots (row -1 = empty); skips a row already present.

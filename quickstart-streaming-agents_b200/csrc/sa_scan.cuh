@@ -32,6 +32,8 @@ constexpr int kUmmaK = 16;
 constexpr int kScanThreads = 256;  // w0 TMA, w1 MMA, w2 TMEM alloc, w3 idle, w4..7 epilogue
 constexpr int kTmemCols = 512;
 constexpr int kChunk = 32;         // TMEM columns per tcgen05.ld
+constexpr int kWin = 16;           // tile lanes whose second-best scores an epilogue thread combines into a bound
+constexpr int kWinWarmTiles = 16;  // the window is read on every one of a lane's first tiles, later only after a slow one
 
 // kMode of the scan kernel
 constexpr int kModeProd = 0;   // production
@@ -84,6 +86,9 @@ struct ScanParams {
   int pace_max;           // cap of that delay
   unsigned* thr_shared;   // [nqb*128*kCG] per-query lower bound on the kKL-th best score, order-preserving keys
                           // (zero at launch), or nullptr: lanes then learn their thresholds alone
+  unsigned* lane2;        // [tl_count][nqb*128*kCG] each lane's SECOND-best score per query (keys, zero at launch), or
+                          // nullptr.  kKL/2 lanes with two rows >= x each are kKL rows >= x: a much tighter bound than
+                          // any single lane's kKL-th best while the lists are young (window_bound below)
   long long* dbg_times;   // optional [gridDim.x][2]: globaltimer at CTA start / end (ns), for drift studies
   float* dbg_dots;        // kModeDots only: raw accumulators of (unit 0 .. nqb-1, tile dbg_tile) [nqb*128*kCG][256]
   int dbg_tile;
@@ -161,6 +166,45 @@ __host__ __device__ __forceinline__ void list_insert(float (&sc)[kKL], int (&id)
   }
 }
 
+// The window bound.  Every tile lane publishes, per query, the SECOND best score it holds.  If kKL/2 different lanes each
+// hold two rows scoring >= x, kKL rows score >= x (lanes own disjoint rows), so no row scoring < x is in the query's
+// global top-kKL: x = the (kKL/2)-th largest of the lanes' second bests is a valid shared bound.  After t tiles per
+// lane it sits near the top 1.7/(256 t) of the scores, the best single lane's kKL-th best near 9/(256 t): about five
+// times fewer values pass it, which is what the first tiles of a short scan spend their time on.  16 keys, bitonic
+// network (80 compare-exchanges, branch-free; key 0 = nothing published sorts last, so an early window yields 0 = no bound).
+__host__ __device__ __forceinline__ void sort16_desc(unsigned (&x)[kWin]) {
+  static_assert(kWin == 16, "the network below is the 16-input bitonic sorter");
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int k = 2; k <= 16; k <<= 1) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+      for (int i = 0; i < 16; ++i) {
+        const int l = i ^ j;
+        if (l > i) {
+          const unsigned a = x[i], b = x[l];
+          const unsigned hi = a > b ? a : b, lo = a > b ? b : a;
+          const bool desc = (i & k) == 0;
+          x[i] = desc ? hi : lo;
+          x[l] = desc ? lo : hi;
+        }
+      }
+    }
+  }
+}
+template <int kKL>
+__host__ __device__ __forceinline__ unsigned window_bound(unsigned (&x)[kWin]) {
+  static_assert(kKL / 2 <= kWin, "the window must hold kKL/2 lanes");
+  sort16_desc(x);
+  return x[kKL / 2 - 1];
+}
+
 // One query's candidate list as an epilogue thread holds it: all indices are compile-time, so it lives in registers.
 template <int kKL>
 struct TopList {
@@ -187,7 +231,7 @@ struct TopList {
   // a bound published by another tile lane becomes visible
   __host__ __device__ __forceinline__ void apply_shared(unsigned key) {
     if (key != 0u) {
-      thr_floor = float_below(key_to_float(key));
+      thr_floor = max_nn(thr_floor, float_below(key_to_float(key)));  // bounds only ever tighten
       thr = max_nn(thr, thr_floor);
     }
   }
@@ -518,9 +562,22 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     };
     if (tl < walk_tiles) fetch_ic(tl * p.tile_stride);
 
+    // Window bound (see window_bound): this thread's slot in the lanes' second-best table, and the kWin lanes it reads.
+    const bool win_on = p.lane2 != nullptr && TL >= kWin && query < p.nq;
+    const size_t win_stride = static_cast<size_t>(p.nqb) * kRowsPerQb;
+    unsigned* const win_q = win_on ? p.lane2 + query : nullptr;
+    float pub2 = -INFINITY;   // last second-best published
+    unsigned nx2[kWin];       // the window as read at the end of the previous accumulator
+    bool have2 = false;
+
     long long w_tfull = 0, busy = 0, slow_chunks = 0;
     int it = 0;
     for (int ti = tl; ti < walk_tiles; ti += TL, ++it) {
+      if (have2) {  // in the shadow of the wait for the MMA
+        const unsigned kb = window_bound<kKL>(nx2);
+        L.nxt_key = kb > L.nxt_key ? kb : L.nxt_key;
+        have2 = false;
+      }
       const int t = ti * p.tile_stride;
       const float qnan = __int_as_float(0x7fc00000);
       auto sc = [&](float x) { return x > 0.f ? x : qnan; };
@@ -555,6 +612,26 @@ sa_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         w_tfull += c1 - c0;
         busy += clock64() - c1;
         slow_chunks += slow;
+      }
+      // accumulator released: publish this lane's second best and, while the lists are young (or whenever a warp just
+      // paid for insertions), fetch the window for the next accumulator's bound
+      if (p.lane2 != nullptr && TL >= kWin) {
+        const bool fetch = (it < kWinWarmTiles) || __any_sync(0xffffffffu, slow > 0);
+        if (win_on) {
+          if (L.sc[1] > pub2) {
+            pub2 = L.sc[1];
+            st_relaxed_gpu_u32(win_q + static_cast<size_t>(tl) * win_stride, float_to_key(pub2));
+          }
+          if (fetch && ti + TL < walk_tiles) {
+#pragma unroll
+            for (int i = 0; i < kWin; ++i) {
+              int ln = tl + i;
+              ln -= (ln >= TL) ? TL : 0;
+              nx2[i] = ld_relaxed_gpu_u32(win_q + static_cast<size_t>(ln) * win_stride);
+            }
+            have2 = true;
+          }
+        }
       }
     }
 

@@ -122,6 +122,9 @@ __device__ __forceinline__ unsigned ld_relaxed_gpu_u32(const unsigned* p) {
 __device__ __forceinline__ void st_relaxed_gpu(int* p, int v) {
   asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void st_relaxed_gpu_u32(unsigned* p, unsigned v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // ----------------------------------------------------------------------------------------------
 // Cluster

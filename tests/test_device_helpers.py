@@ -102,3 +102,40 @@ def test_shared_floor_drops_only_what_cannot_matter(lib):
     held = set(got_r.tolist())
     assert drop >= max(s[r] for r in range(400) if r not in held)
     assert ((s == x) & (rows >= 50)).sum() > 0                         # the data really contains ties with the bound
+
+
+def test_window_bound_is_an_order_statistic_of_the_lanes_second_bests(lib):
+    """The epilogue's 16-input network sorts any 16 keys, and the bound it returns is the (KL/2)-th largest -- with
+    unpublished lanes (key 0) counting as 'nothing there yet'."""
+    g = np.random.default_rng(5)
+    w = g.integers(0, 2 ** 32, size=(4000, 16), dtype=np.uint64).astype(np.uint32)
+    w[:500] = g.integers(0, 4, size=(500, 16)).astype(np.uint32)       # heavy ties and zeros
+    w[500:1000, ::2] = 0                                               # half of the lanes have published nothing
+    w[1000] = 0
+    w[1001] = 0xFFFFFFFF
+    for kl in (16, 32):
+        out = np.empty(len(w), np.uint32); srt = np.empty_like(w)
+        assert lib.sa_debug_window_bound(ptr(w), len(w), kl, ptr(out), ptr(srt)) == 0
+        ref = -np.sort(-w.astype(np.int64), axis=1)
+        assert (srt.astype(np.int64) == ref).all()
+        assert (out.astype(np.int64) == ref[:, kl // 2 - 1]).all()
+    assert out[1000] == 0 and (out[500:1000] == 0).all()               # KL = 32 needs all 16 lanes
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(0, 2 ** 31), st.sampled_from([16, 32]), st.integers(1, 6))
+def test_window_bound_never_exceeds_the_global_kl_th_best(lib, seed, kl, tiles):
+    """Validity of the bound on simulated lanes: 16 lanes with disjoint rows, each holding the list rule's result over
+    its rows so far; the bound built from their second bests never exceeds the KL-th best score over all their rows, so
+    dropping rows below it cannot lose a member of the global top-KL (ties are admitted by the floor's >= rule)."""
+    g = np.random.default_rng(seed)
+    lanes = [np.round(g.standard_normal(tiles * 64), 2).astype(np.float32) for _ in range(16)]   # coarse: many ties
+    second = np.array([np.sort(x)[::-1][1] for x in lanes], np.float32)
+    key = np.empty(16, np.uint32); back = np.empty(16, np.float32); below = np.empty(16, np.float32)
+    assert lib.sa_debug_float_keys(ptr(second), 16, ptr(key), ptr(back), ptr(below)) == 0
+    out = np.empty(1, np.uint32)
+    assert lib.sa_debug_window_bound(ptr(key), 1, kl, ptr(out), None) == 0
+    bound = second[key == out[0]][0]
+    allv = np.sort(np.concatenate(lanes))[::-1]
+    assert bound <= allv[kl - 1]
+    assert (allv >= bound).sum() >= kl

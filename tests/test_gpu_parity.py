@@ -385,8 +385,11 @@ def test_sampling_prepass_keeps_answers_and_tames_an_ascending_corpus(bf, cg):
         ix.append_bf16_bits(c)
         ix.set_option("cta_group", cg)
         rs, ri = bf.cosine_topk_fast(q[:40], [(0, c)], k)
-        for ps in (0, 2, 8):
-            ix.set_option("presample", ps)
+        # the pre-pass is measured against the plain shared threshold (the window bound, which also softens this
+        # case, switched off); "wb" = the default configuration, no pre-pass
+        for ps in (0, 2, 8, "wb"):
+            ix.set_option("presample", 0 if ps == "wb" else ps)
+            ix.set_option("window_bound", 1 if ps == "wb" else 0)
             s, i = ix.search(dev(q), k)
             torch.cuda.synchronize()
             assert (i.cpu().numpy()[:40] == ri).all(), (name, ps)
@@ -397,6 +400,7 @@ def test_sampling_prepass_keeps_answers_and_tames_an_ascending_corpus(bf, cg):
         ix.close()
     assert times[("ascending", 8)] < 0.7 * times[("ascending", 0)], times      # the pre-pass removes the blow-up ...
     assert times[("ascending", 8)] < 2.0 * times[("random", 0)], times         # ... to within 2x of the random order
+    assert times[("ascending", "wb")] < 1.1 * times[("ascending", 0)], times   # the window bound never makes it worse
 
 
 def test_drift_control_and_mapping_options_do_not_change_answers(bf):
@@ -410,10 +414,38 @@ def test_drift_control_and_mapping_options_do_not_change_answers(bf):
     for cg in (1, 2):
         for gain, drift, umap in ((0, 1, 0), (16, 1, 0), (64, 0, 1), (4096, 0, 0)):
             ix.set_option("pace_gain", gain); ix.set_option("max_drift", drift); ix.set_option("unit_map", umap)
+            ix.set_option("window_bound", 0 if gain == 16 else 1)
             check(ix, q, c, k, cg)
     scan, total, m = ix.timing_mean(16)
     assert m == 8 and 0 < scan <= total
     ix.close()
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+def test_window_bound_with_ties_scattered_over_every_lane(bf, cg):
+    """The window bound (kKL/2 lanes holding two rows >= x each) at its sharpest: exact copies of one row scattered over
+    the whole corpus, so that most lanes' second best EQUALS the best score and the bound equals the score to keep.  Ties
+    must still resolve to the lowest rows, for k up to the list length, on short scans (two tiles per lane) and long."""
+    from qsa_b200.engine import VectorIndex
+    dim = 256
+    for n, every in ((148 * 256 * 2 + 77, 211), (200_000, 97)):
+        c = bf.synth_rows(71, 0, n, dim)
+        base = c[5].copy()
+        c[every::every] = base                                          # hundreds of copies, a few per lane
+        q = bf.synth_queries(72, 100, dim, c)
+        q[0] = base
+        b32 = bf.bf16_bits_to_f32(base)
+        g = np.random.default_rng(73)
+        for r in range(1, 6):                                           # near the crowd: every copy ties exactly
+            q[r] = bf.f32_to_bf16_bits(b32 + np.float32(0.2 * np.abs(b32).mean()) * g.standard_normal(dim).astype(np.float32))
+        ix = VectorIndex(dim=dim, capacity=n, max_batch=128, max_k=28)
+        ix.append_bf16_bits(c)
+        for wb in (1, 0):
+            ix.set_option("window_bound", wb)
+            for k in (10, 16, 20):
+                s, i = check(ix, q, c, k, cg)
+                assert i[0, 0] == 5 and i[0, 1:].tolist() == [every * (j + 1) for j in range(k - 1)]
+        ix.close()
 
 
 def test_full_size_properties_10M(bf):

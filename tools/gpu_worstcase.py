@@ -8,7 +8,7 @@ on exchangeable data, a value beats the running threshold with probability ~ kKL
             source), queries near some of the centres
 
 For each, the production scan kernel is timed against the same rows in random order, with and without the sampled
-threshold pre-pass (option "presample").  Answers are compared with the shuffled run (same set of rows => same scores).
+threshold pre-pass (option "presample"), or with any other engine option swept (--option window_bound --presample 0,1).  Answers are compared with the shuffled run (same set of rows => same scores).
 
     python tools/gpu_worstcase.py [--rows 4000000] [--batches 128,1024] [--out gpurun_out/worstcase.json]
 """
@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--batches", default="128,1024")
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--presample", default="0,64", help="values of the engine option to compare")
+    ap.add_argument("--option", default="presample", help="the engine option those values are for (e.g. window_bound)")
     ap.add_argument("--noise", type=float, default=0.6, help="spread of the queries around their centroid (0.1 = near-duplicates)")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
@@ -96,11 +97,11 @@ def main():
             pass
         base = {}
         for ps in [int(x) for x in a.presample.split(",")]:
-            ix.set_option("presample", ps)
+            ix.set_option(a.option, ps)
             scan, total, s64, i = timed(ix, q_near, k)
             base[ps] = (scan, total)
             ref_scores = s64.clone()
-            res.append({"batch": B, "case": "random order", "presample": ps, "scan_ms": scan, "search_ms": total})
+            res.append({"batch": B, "case": "random order", a.option: ps, "scan_ms": scan, "search_ms": total})
             print(json.dumps(res[-1]), flush=True)
         order = torch.argsort(sim_to(q_near.float().mean(0)))
         tmp = torch.empty_like(ix.rows)
@@ -112,10 +113,10 @@ def main():
         ix.lib.sa_corpus_reset(ix._h)
         ix.commit(0, n)
         for ps in [int(x) for x in a.presample.split(",")]:
-            ix.set_option("presample", ps)
+            ix.set_option(a.option, ps)
             scan, total, s64, i = timed(ix, q_near, k)
             same = bool(torch.equal(s64, ref_scores))          # same set of rows => identical sorted cosine lists
-            res.append({"batch": B, "case": "ascending similarity to the batch centroid", "presample": ps, "scan_ms": scan,
+            res.append({"batch": B, "case": "ascending similarity to the batch centroid", a.option: ps, "scan_ms": scan,
                         "search_ms": total, "slowdown_vs_random": total / base[ps][1], "same_scores_as_random_order": same})
             print(json.dumps(res[-1]), flush=True)
         # ---- clustered embeddings stored cluster by cluster
@@ -124,11 +125,11 @@ def main():
                a.noise * torch.randn((B, dim), generator=g, device=dev)).to(torch.bfloat16)
         base = {}
         for ps in [int(x) for x in a.presample.split(",")]:
-            ix.set_option("presample", ps)
+            ix.set_option(a.option, ps)
             scan, total, s64, i = timed(ix, q_c, k)
             base[ps] = (scan, total)
             ref_scores = s64.clone()
-            res.append({"batch": B, "case": "clustered, random order", "presample": ps, "scan_ms": scan, "search_ms": total})
+            res.append({"batch": B, "case": "clustered, random order", a.option: ps, "scan_ms": scan, "search_ms": total})
             print(json.dumps(res[-1]), flush=True)
         # cluster by cluster: sort rows by their nearest-centre id (approximated by the sign pattern of a projection)
         key = sim_to(torch.randn(dim, generator=g, device=dev))
@@ -141,9 +142,9 @@ def main():
         ix.lib.sa_corpus_reset(ix._h)
         ix.commit(0, n)
         for ps in [int(x) for x in a.presample.split(",")]:
-            ix.set_option("presample", ps)
+            ix.set_option(a.option, ps)
             scan, total, s64, i = timed(ix, q_c, k)
-            res.append({"batch": B, "case": "clustered, sorted along a random direction", "presample": ps, "scan_ms": scan,
+            res.append({"batch": B, "case": "clustered, sorted along a random direction", a.option: ps, "scan_ms": scan,
                         "search_ms": total, "slowdown_vs_random": total / base[ps][1],
                         "same_scores_as_random_order": bool(torch.equal(s64, ref_scores))})
             print(json.dumps(res[-1]), flush=True)
