@@ -151,6 +151,9 @@ class Lab2Pipeline:
         self._metrics_t0 = time.time()
         self._metrics_q0 = 0
         self._sink_dirty = False
+        # further statements over the same table, run at the end of every pass (pipeline/lateral.py: the Lab3 / Lab4
+        # form of the operator, joined LATERALly onto an upstream stream)
+        self.extra_stages: list = []
 
     # ------------------------------------------------------------------ helpers
     def _decode_all(self, topic: str, msgs):
@@ -585,7 +588,10 @@ class Lab2Pipeline:
             moved += n
             if n == 0:
                 break
-        return moved + self.stage_queries() + self.stage_search() + self.stage_response()
+        moved += self.stage_queries() + self.stage_search() + self.stage_response()
+        for st in self.extra_stages:
+            moved += st.run_once()
+        return moved
 
     def run_until_idle(self, max_passes: int = 1000) -> int:
         total = 0

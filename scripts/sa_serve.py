@@ -40,6 +40,10 @@ def main(argv=None) -> int:
     ap.add_argument("--score-mode", default="cosine", choices=["cosine", "atlas"],
                     help="score_i on search_results: raw cosine, or (1 + cos) / 2 as MongoDB Atlas reports it "
                          "(the reference's index, assets/pre-setup/MongoDB-Setup.md:72-83); the ranking is the same")
+    ap.add_argument("--lateral", action="append", default=[], choices=["lab3", "lab4"],
+                    help="also run the operator joined onto an upstream stream, over the same table: lab3 = "
+                         "anomalies_per_zone -> anomalies_enriched (LAB3-Walkthrough.md:225-375), lab4 = claims_to_investigate "
+                         "-> claims_to_investigate_with_policies (LAB4-Walkthrough.md:251-309); repeatable")
     ap.add_argument("--once", action="store_true", help="process everything pending, print stats, exit")
     ap.add_argument("--snapshot-dir", default=None,
                     help="checkpoint directory: loaded at start if it holds a checkpoint, written periodically and on exit")
@@ -63,6 +67,11 @@ def main(argv=None) -> int:
         print(f"resumed {table.load(a.snapshot_dir)} rows from {a.snapshot_dir} at {table.source_offsets}", file=sys.stderr)
     pipe = Lab2Pipeline(resolve_log_dir(a.log_dir), table, k=a.k, max_batch=a.max_batch, score_mode=a.score_mode,
                         metrics_file=a.metrics_file)
+    if a.lateral:
+        from qsa_b200.pipeline import lateral
+        make = {"lab3": lateral.lab3_anomalies_enriched, "lab4": lateral.lab4_claims_with_policies}
+        for name in a.lateral:
+            pipe.extra_stages.append(make[name](pipe.log_dir, table, score_mode=a.score_mode, max_batch=a.max_batch))
 
     def on_term(signum, frame):      # SIGTERM takes the same exit path as Ctrl-C: stats, final checkpoint
         raise KeyboardInterrupt
