@@ -172,10 +172,10 @@ struct sa_engine {
   int opt_cta_group = 0;
   int opt_max_launch_qblocks = 0;
   int opt_max_drift = -1;  // -1 = auto (1 tile)
-  int opt_pace_gain = -1;  // -1 = auto (16 cycles/tile for CTA pairs, 32 for single CTAs), 0 = off
+  int opt_pace_gain = -1;  // -1 = auto (64 cycles/tile for CTA pairs, 32 for single CTAs), 0 = off
   int opt_pace_max = -1;   // -1 = auto (8 x gain)
   int opt_unit_map = 0;
-  int opt_list_len = 0;    // 0 = auto (16 when k <= 12, else 32)
+  int opt_list_len = 0;    // 0 = auto (16 when k <= 16, else 32)
   int opt_wait_hint_ns = -1;  // suspend-time hint of the epilogue's mbarrier waits (-1 = auto, 0 = plain polling)
   int opt_presample = -1;  // tile stride of the sampling pre-pass that seeds the shared thresholds (-1 = auto, 0 = off)
   int opt_force_fix = 0;   // test hook: every (query, lane) goes through the exact fallback scan
