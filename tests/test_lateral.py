@@ -229,3 +229,44 @@ def test_lab4_statement_on_gpu(tmp_path):
         assert [rec[f"policy_chunk_{i}"] for i in (1, 2, 3)] == [h.chunk for h in hits]
         assert [rec[f"policy_score_{i}"] for i in (1, 2, 3)] == [h.score for h in hits]
     ix.close()
+
+
+def test_statement_over_the_kafka_adapter_matches_the_file_log(tmp_path, monkeypatch):
+    """The stage only speaks the transport interface: over transport.kafka (confluent_kafka stand-in) it writes the same
+    bytes as over the file log and commits the source offsets it has covered."""
+    import sys
+
+    import fake_confluent_kafka as fck
+    from qsa_b200.transport import filelog, kafka
+    monkeypatch.setitem(sys.modules, "confluent_kafka", fck)
+    fck.reset()
+    g = np.random.default_rng(9)
+    dim = 32
+    outs = {}
+    for name, mod, conf in (("file", filelog, None), ("kafka", kafka, {"bootstrap.servers": "fake:9092"})):
+        logd = str(tmp_path / name)
+        table = VectorTable(OracleIndex(dim))
+        g = np.random.default_rng(9)
+        table.upsert_many([f"d{i}" for i in range(30)], [f"chunk {i}" for i in range(30)],
+                          g.standard_normal((30, dim)).astype(np.float32),
+                          metadata=[{"title": f"T{i}", "pages": str(i)} for i in range(30)])
+        schema = {**lateral.ANOMALIES_PER_ZONE_VALUE, "fields": lateral.ANOMALIES_PER_ZONE_VALUE["fields"] + [
+            {"name": "embedding", "type": ["null", {"type": "array", "items": ["null", "float"]}], "default": None}]}
+        sid = SchemaRegistry(logd).register("zones-value", schema)
+        prod = mod.Producer(dict(conf or {}, **{"log.dir": logd}))
+        for i in range(7):
+            rec = {"pickup_zone": f"Z{i}", "window_time": 1000 * i, "request_count": i, "expected_requests": 1.0, "is_surge": True,
+                   "embedding": [float(x) for x in g.standard_normal(dim).astype(np.float32)]}
+            prod.produce("zones", key=f"k{i}", value=avro.frame(sid, avro.encode(schema, rec)))
+        prod.flush()
+        st = lateral.LateralSearch(logd, table, "zones", "zones_with_docs", columns={"document_id": "doc", "title": "title", "score": "s"},
+                                   k=3, n_out=2, carry=("pickup_zone", "window_time"), max_batch=4, transport=mod, client_conf=conf)
+        assert st.run_until_idle() == 7
+        c = mod.Consumer(dict(conf or {}, **{"log.dir": logd, "group.id": "check", "enable.auto.commit": False}))
+        c.subscribe(["zones_with_docs"])
+        outs[name] = [(m.key(), m.value()) for m in c.consume(100, 0.0)]
+    assert len(outs["file"]) == 7 and outs["kafka"] == outs["file"]
+    assert fck._BROKER["groups"]["sa-lateral"][("zones", 0)] == 7
+    rec = avro.decode(SchemaRegistry(str(tmp_path / "file")).get(struct.unpack_from(">I", outs["file"][0][1], 1)[0]), outs["file"][0][1], 5)
+    assert list(rec) == ["pickup_zone", "window_time", "doc_1", "title_1", "s_1", "doc_2", "title_2", "s_2"]
+    assert rec["title_1"] == "T" + rec["doc_1"][1:] and rec["s_1"] >= rec["s_2"]
