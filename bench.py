@@ -752,11 +752,11 @@ def pipeline_e2e(env, index_like, n_total, dim, B, k, q_bits, est_batch_s, min_t
         real_consume = c.consume_raw
         budget = [2]
 
-        def limited(nmax):
+        def limited(nmax, out=None):
             if budget[0] <= 0:
                 return None
             budget[0] -= 1
-            return real_consume(nmax)
+            return real_consume(nmax, out)
         c.consume_raw = limited
         assert pipe.stage_search() == 2 * B
         c.consume_raw = real_consume

@@ -4,14 +4,63 @@
 #include "../../include/sa_api.h"
 #include "../../include/sa_wire.h"
 
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
+#include <vector>
 
 extern "C" int sa_internal_fail(int rc, const char* fmt, ...);  // sa_api.cu: sets sa_last_error()
 
 namespace {
 
 constexpr uint32_t kNullLen = 0xFFFFFFFFu;
+
+// `dim` items of an Avro array of ["null","float"]: true iff every item is the float branch (byte 2) and finite; the
+// floats land in dst.  No early exit, so the loop unrolls and pipelines (a batch of 1024 x 1536-d embeddings is 1.6 M
+// items: this loop is the decode).  The caller has checked that 5 * dim bytes are readable and zero-fills dst on failure.
+inline bool copy_float_items(const uint8_t* p, int dim, float* dst) {
+  uint32_t bad = 0;
+  for (int j = 0; j < dim; ++j) {
+    uint32_t bits;
+    memcpy(&bits, p + 5 * static_cast<size_t>(j) + 1, 4);
+    bad |= static_cast<uint32_t>(p[5 * static_cast<size_t>(j)] ^ 2u);
+    bad |= static_cast<uint32_t>((bits & 0x7F800000u) == 0x7F800000u);   // inf or NaN
+    memcpy(dst + j, &bits, 4);
+  }
+  return bad == 0;
+}
+
+// Records of a batch are independent: decode them on a few threads (SA_WIRE_THREADS, default 4; small batches stay on
+// the caller's thread).  Plain std::thread -- OpenMP would be pinned to one thread by torchrun's OMP_NUM_THREADS=1.
+int wire_threads() {
+  static const int n = [] {
+    const char* e = getenv("SA_WIRE_THREADS");
+    int v = e ? atoi(e) : 4;
+    const unsigned hw = std::thread::hardware_concurrency();
+    if (hw > 0) v = std::min<int>(v, static_cast<int>(hw));
+    return std::max(1, std::min(v, 16));
+  }();
+  return n;
+}
+template <typename F>
+void for_each_record(int n, F&& body) {   // body(first, last)
+  const int t = (n >= 256) ? std::min(wire_threads(), n / 128) : 1;
+  if (t <= 1) {
+    body(0, n);
+    return;
+  }
+  std::vector<std::thread> th;
+  th.reserve(t - 1);
+  const int per = (n + t - 1) / t;
+  for (int i = 1; i < t; ++i) {
+    const int lo = std::min(n, i * per), hi = std::min(n, (i + 1) * per);
+    if (lo < hi) th.emplace_back([&body, lo, hi] { body(lo, hi); });
+  }
+  body(0, std::min(n, per));
+  for (auto& x : th) x.join();
+}
 
 inline uint32_t rd_u32(const uint8_t* p) {
   uint32_t v;
@@ -97,8 +146,8 @@ int sa_wire_decode_queries_embed(const uint8_t* buf, const uint64_t* value_off, 
                                  uint8_t* status, int* n_ok) {
   if (!buf || !value_off || !value_len || !out_vec || !text_off || !text_len || !status || n < 0 || dim <= 0)
     return sa_internal_fail(SA_ERR_ARG, "sa_wire_decode_queries_embed: bad argument");
-  int ok = 0;
-  for (int i = 0; i < n; ++i) {
+  for_each_record(n, [&](int first, int last) {
+  for (int i = first; i < last; ++i) {
     float* dst = out_vec + static_cast<size_t>(i) * dim;
     status[i] = 1;
     text_off[i] = 0;
@@ -123,34 +172,24 @@ int sa_wire_decode_queries_embed(const uint8_t* buf, const uint64_t* value_off, 
       int64_t cnt;
       if (!read_long(p, end, &cnt, &p) || cnt != dim) break;  // one block of exactly dim items
       if (end - p != static_cast<int64_t>(dim) * 5 + 1) break;
-      bool items_ok = true;
-      for (int j = 0; j < dim; ++j) {
-        if (p[0] != 2) {  // null item
-          items_ok = false;
-          break;
-        }
-        float f;
-        memcpy(&f, p + 1, 4);
-        if (!std::isfinite(f)) {
-          items_ok = false;
-          break;
-        }
-        dst[j] = f;
-        p += 5;
-      }
-      if (!items_ok || *p != 0) break;  // end-of-array marker
+      if (!copy_float_items(p, dim, dst)) break;  // a null item or a non-finite value
+      p += static_cast<size_t>(dim) * 5;
+      if (*p != 0) break;  // end-of-array marker
       text_off[i] = static_cast<uint64_t>(text - buf);
       text_len[i] = static_cast<uint32_t>(tl);
       good = true;
     } while (false);
-    if (good) {
+    if (good)
       status[i] = 0;
-      ++ok;
-    } else {
+    else
       memset(dst, 0, sizeof(float) * dim);
-    }
   }
-  if (n_ok) *n_ok = ok;
+  });
+  if (n_ok) {
+    int ok = 0;
+    for (int i = 0; i < n; ++i) ok += status[i] == 0;
+    *n_ok = ok;
+  }
   return SA_OK;
 }
 
@@ -199,8 +238,8 @@ int sa_wire_decode_documents_embed(const uint8_t* buf, const uint64_t* value_off
   if (!buf || !value_off || !value_len || !out_vec || !id_off || !id_len || !chunk_off || !chunk_len || !meta_off ||
       !meta_len || !status || n < 0 || dim <= 0)
     return sa_internal_fail(SA_ERR_ARG, "sa_wire_decode_documents_embed: bad argument");
-  int ok = 0;
-  for (int i = 0; i < n; ++i) {
+  for_each_record(n, [&](int first, int last) {
+  for (int i = first; i < last; ++i) {
     float* dst = out_vec + static_cast<size_t>(i) * dim;
     status[i] = 1;
     id_off[i] = chunk_off[i] = meta_off[i] = 0;
@@ -246,18 +285,9 @@ int sa_wire_decode_documents_embed(const uint8_t* buf, const uint64_t* value_off
       int64_t cnt;
       if (!read_long(p, end, &cnt, &p) || cnt != dim) break;
       if (end - p < static_cast<int64_t>(dim) * 5 + 1) break;
-      bool items_ok = true;
-      for (int j = 0; j < dim; ++j) {
-        float f;
-        memcpy(&f, p + 1, 4);
-        if (p[0] != 2 || !std::isfinite(f)) {
-          items_ok = false;
-          break;
-        }
-        dst[j] = f;
-        p += 5;
-      }
-      if (!items_ok || *p++ != 0) break;
+      if (!copy_float_items(p, dim, dst)) break;
+      p += static_cast<size_t>(dim) * 5;
+      if (*p++ != 0) break;
       // metadata columns (terraform/lab4-pubsec-fraud-agents/main.tf:271-289): validated here, decoded lazily by the host
       const uint8_t* m0 = p;
       if (!skip_nullable_string(p, end) || !skip_nullable_string(p, end) || !skip_nullable_string(p, end) ||
@@ -272,14 +302,17 @@ int sa_wire_decode_documents_embed(const uint8_t* buf, const uint64_t* value_off
       meta_len[i] = static_cast<uint32_t>(end - m0);
       good = true;
     } while (false);
-    if (good) {
+    if (good)
       status[i] = 0;
-      ++ok;
-    } else {
+    else
       memset(dst, 0, sizeof(float) * dim);
-    }
   }
-  if (n_ok) *n_ok = ok;
+  });
+  if (n_ok) {
+    int ok = 0;
+    for (int i = 0; i < n; ++i) ok += status[i] == 0;
+    *n_ok = ok;
+  }
   return SA_OK;
 }
 

@@ -146,6 +146,7 @@ class Lab2Pipeline:
                 if native:
                     raise
         self._qbuf = None          # two query staging buffers (page-locked when the index can DMA from them)
+        self._rbuf = [None, None]  # two reusable read buffers for the partition-log slices of the native search stage
         self._lat_ms: list[float] = []
         self._metrics_file, self._metrics_every_s = metrics_file, metrics_every_s
         self._metrics_t0 = time.time()
@@ -384,9 +385,11 @@ class Lab2Pipeline:
         else through the generic codec (which also quarantines), in place, so the batch keeps its order."""
         topic, part, first, n, data = raw
         lib, dim = self._wire, self.table.index.dim
+        data = np.frombuffer(data, np.uint8)       # bytes, or a view of the reusable read buffer: no copy either way
+        dptr = data.ctypes.data
         voff = np.empty(n, np.uint64)
         vlen = np.empty(n, np.uint32)
-        rc = lib.sa_wire_split_log(data, len(data), n, voff.ctypes.data, vlen.ctypes.data, None, None, None)
+        rc = lib.sa_wire_split_log(dptr, len(data), n, voff.ctypes.data, vlen.ctypes.data, None, None, None)
         if rc:
             raise avro.AvroError("corrupt log slice: " + lib.sa_last_error().decode())
         vecs = self._query_buffers()[slot]
@@ -394,7 +397,7 @@ class Lab2Pipeline:
         tlen = np.empty(n, np.uint32)
         status = np.empty(n, np.uint8)
         n_ok = C.c_int()
-        rc = lib.sa_wire_decode_queries_embed(data, voff.ctypes.data, vlen.ctypes.data, n, dim,
+        rc = lib.sa_wire_decode_queries_embed(dptr, voff.ctypes.data, vlen.ctypes.data, n, dim,
                                               self.codec.schema_id("queries_embed"), vecs.ctypes.data, toff.ctypes.data,
                                               tlen.ctypes.data, status.ctypes.data, C.byref(n_ok))
         if rc:
@@ -404,7 +407,7 @@ class Lab2Pipeline:
             extra = bytearray()
             keep = np.ones(n, bool)
             for i in np.flatnonzero(status).tolist():
-                value = None if vlen[i] == 0xFFFFFFFF else data[int(voff[i]):int(voff[i]) + int(vlen[i])]
+                value = None if vlen[i] == 0xFFFFFFFF else data[int(voff[i]):int(voff[i]) + int(vlen[i])].tobytes()
                 m = Message(topic, part, first + i, None, value, 0)
                 got = self._decode_all("queries_embed", [m])
                 vec = got[0][1].get("embedding") if got else None
@@ -421,7 +424,7 @@ class Lab2Pipeline:
                     tlen[i] = len(qb)
                     extra += qb
             if extra:
-                text_buf = data + bytes(extra)
+                text_buf = np.frombuffer(data.tobytes() + bytes(extra), np.uint8)
             if not keep.all():
                 good = np.flatnonzero(keep)
                 vecs[:len(good)] = vecs[good]
@@ -436,7 +439,7 @@ class Lab2Pipeline:
         k = score.shape[1]
         rec_off = np.empty(n + 1, np.uint64)
         need = C.c_uint64()
-        args = (n, k, schemas.RESULTS_PER_QUERY, self.codec.schema_id("search_results"), text_buf, toff.ctypes.data,
+        args = (n, k, schemas.RESULTS_PER_QUERY, self.codec.schema_id("search_results"), text_buf.ctypes.data, toff.ctypes.data,
                 tlen.ctypes.data, score.ctypes.data, rows.ctypes.data, t.arena_document_id.data.ctypes.data,
                 t.arena_document_id.off.ctypes.data, t.arena_chunk.data.ctypes.data, t.arena_chunk.off.ctypes.data, len(t),
                 1 if self.score_mode == "atlas" else 0, int(time.time() * 1000))
@@ -483,9 +486,11 @@ class Lab2Pipeline:
         pipelined = hasattr(index, "search_host_submit")
         total, slot, pending = 0, 0, None
         while True:
-            raw = c.consume_raw(self.max_batch)
+            raw = c.consume_raw(self.max_batch, self._rbuf[slot])
             batch = None
             if raw is not None:
+                if self._rbuf[slot] is None or len(raw[4]) > len(self._rbuf[slot]):   # size the buffer to the slices seen
+                    self._rbuf[slot] = np.empty(len(raw[4]) + len(raw[4]) // 8 + 4096, np.uint8)
                 total += raw[3]
                 t_in = time.perf_counter()
                 n, vecs, text_buf, toff, tlen = self._decode_raw_batch(raw, slot)
