@@ -13,6 +13,8 @@
  *   file-log record        u32 key_len (0xFFFFFFFF = null) | key | u32 value_len | value | i64 timestamp_ms, little-endian
  *                          (quickstart-streaming-agents_b200/transport/filelog.py).
  * Every function returns 0 or a negative sa_status (sa_api.h); sa_last_error() has the detail.
+ * The two batch decoders spread the records of a large batch over a few threads (environment SA_WIRE_THREADS, default 4,
+ * 1 = the caller's thread only); the threads live only for the duration of the call.
  */
 #ifndef SA_WIRE_H_
 #define SA_WIRE_H_
