@@ -128,3 +128,28 @@ def test_kafka_adapter_drives_the_same_pipeline(tmp_path, monkeypatch):
         outs[name] = [m.value() for m in c.consume(100, 0.0)]
     assert len(outs["file"]) == 25 and outs["kafka"] == outs["file"]
     assert fck._BROKER["groups"]["sa-lab2"][("queries_embed", 0)] == 25
+
+
+def test_raw_batch_reads_into_a_reusable_buffer(tmp_path):
+    """consume_raw(out=buffer): the slice lands in the caller's buffer when it fits (a view of its prefix comes back),
+    otherwise a fresh byte string -- the same bytes either way, and positions advance identically."""
+    import numpy as np
+    from qsa_b200.transport.filelog import Consumer, Producer
+    logd = str(tmp_path)
+    p = Producer({"log.dir": logd})
+    vals = [bytes([i % 251]) * (50 + 13 * i) for i in range(40)]
+    for i, v in enumerate(vals):
+        p.produce("t", key=(None if i % 3 else f"k{i}".encode()), value=v)
+    p.flush()
+    plain = Consumer({"log.dir": logd, "group.id": "a"}); plain.subscribe(["t"])
+    buffered = Consumer({"log.dir": logd, "group.id": "b"}); buffered.subscribe(["t"])
+    big, small = np.empty(1 << 16, np.uint8), bytearray(8)
+    for n, out in ((7, big), (9, small), (100, big)):
+        a = plain.consume_raw(n)
+        b = buffered.consume_raw(n, out)
+        assert a[:4] == b[:4] and bytes(a[4]) == bytes(b[4])
+        if out is big:
+            assert isinstance(b[4], memoryview) and bytes(big[:len(b[4])]) == bytes(a[4])     # it really is the caller's buffer
+        else:
+            assert isinstance(b[4], bytes)
+    assert plain.consume_raw(5) is None and buffered.consume_raw(5, big) is None
