@@ -32,6 +32,45 @@ inline bool copy_float_items(const uint8_t* p, int dim, float* dst) {
   return bad == 0;
 }
 
+// Strict UTF-8 (what Python's bytes.decode("utf-8") accepts: no overlong forms, no surrogates, nothing above U+10FFFF).
+// A string the generic codec would refuse to decode must not pass here either -- the record is then handed over and
+// quarantined there, instead of travelling on as bytes nobody can decode.
+inline bool valid_utf8(const uint8_t* s, size_t n) {
+  size_t i = 0;
+  while (i < n) {
+    if (i + 8 <= n) {  // eight ASCII bytes at a time
+      uint64_t w;
+      memcpy(&w, s + i, 8);
+      if (!(w & 0x8080808080808080ull)) {
+        i += 8;
+        continue;
+      }
+    }
+    const uint8_t c = s[i];
+    if (c < 0x80) {
+      ++i;
+    } else if (c < 0xC2) {
+      return false;  // a continuation byte, or the lead of an overlong two-byte form
+    } else if (c < 0xE0) {
+      if (i + 1 >= n || (s[i + 1] & 0xC0) != 0x80) return false;
+      i += 2;
+    } else if (c < 0xF0) {
+      if (i + 2 >= n || (s[i + 1] & 0xC0) != 0x80 || (s[i + 2] & 0xC0) != 0x80) return false;
+      if (c == 0xE0 && s[i + 1] < 0xA0) return false;   // overlong
+      if (c == 0xED && s[i + 1] >= 0xA0) return false;  // UTF-16 surrogates
+      i += 3;
+    } else if (c < 0xF5) {
+      if (i + 3 >= n || (s[i + 1] & 0xC0) != 0x80 || (s[i + 2] & 0xC0) != 0x80 || (s[i + 3] & 0xC0) != 0x80) return false;
+      if (c == 0xF0 && s[i + 1] < 0x90) return false;   // overlong
+      if (c == 0xF4 && s[i + 1] >= 0x90) return false;  // above U+10FFFF
+      i += 4;
+    } else {
+      return false;
+    }
+  }
+  return true;
+}
+
 // Records of a batch are independent: decode them on a few threads (SA_WIRE_THREADS, default 4; small batches stay on
 // the caller's thread).  Plain std::thread -- OpenMP would be pinned to one thread by torchrun's OMP_NUM_THREADS=1.
 int wire_threads() {
@@ -167,6 +206,7 @@ int sa_wire_decode_queries_embed(const uint8_t* buf, const uint64_t* value_off, 
       int64_t tl;
       if (!read_long(p, end, &tl, &p) || tl < 0 || tl > end - p) break;
       const uint8_t* text = p;
+      if (!valid_utf8(text, static_cast<size_t>(tl))) break;
       p += tl;
       if (p >= end || *p++ != 2) break;  // embedding: ["null", array], branch 1
       int64_t cnt;
@@ -202,6 +242,7 @@ inline bool skip_nullable_string(const uint8_t*& p, const uint8_t* end) {
   if (br != 1) return false;
   int64_t n;
   if (!read_long(p, end, &n, &p) || n < 0 || n > end - p) return false;
+  if (!valid_utf8(p, static_cast<size_t>(n))) return false;
   p += n;
   return true;
 }
@@ -270,7 +311,7 @@ int sa_wire_decode_documents_embed(const uint8_t* buf, const uint64_t* value_off
         sl[f] = kNullLen;
         if (br == 1) {
           int64_t tl;
-          if (!read_long(p, end, &tl, &p) || tl < 0 || tl > end - p) {
+          if (!read_long(p, end, &tl, &p) || tl < 0 || tl > end - p || !valid_utf8(p, static_cast<size_t>(tl))) {
             strings_ok = false;
             break;
           }

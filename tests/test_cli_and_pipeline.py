@@ -605,3 +605,41 @@ def test_config1_two_thousand_docs_plumbing_on_cpu(tmp_path):
         assert abs(row["score_1"] - s[r, 0]) < 1e-6 and row["score_1"] >= row["score_2"] >= row["score_3"]
     hits = vector_search_agg(table, "embedding", emb.embed(questions[0]), 10)[0]
     assert [h.row for h in hits] == i[0].tolist()
+
+
+@pytest.mark.parametrize("native", [True, False])
+def test_strings_that_are_not_utf8_are_quarantined_by_both_codecs(tmp_path, native):
+    """A record whose string bytes are not UTF-8 (a corrupted producer, a Latin-1 client) is a poison record: both the
+    native batch path and the generic codec send it to the DLQ and carry on -- in the sink (chunk, document_id, a metadata
+    string) and in the search stage (query text)."""
+    logd = str(tmp_path / "topics")
+    dim = 64
+    table = VectorTable(PipelinedOracleIndex(dim))
+    pipe = Lab2Pipeline(logd, table, embedder=StubEmbedder(dim), k=3, max_batch=8, native=native)
+    g = np.random.default_rng(3)
+
+    def doc(i, **kw):
+        r = {"document_id": f"d{i}", "chunk": f"chunk number {i}", "embedding": g.standard_normal(dim).astype(np.float32)}
+        r.update(kw)
+        return bytearray(pipe.codec.encode("documents_embed", r))
+    docs = [doc(i) for i in range(6)]
+    bad_chunk, bad_id, bad_meta = doc(6), doc(7), doc(8, title="Title eight")
+    bad_chunk[bytes(bad_chunk).find(b"chunk number 6")] = 0xFF
+    bad_id[bytes(bad_id).find(b"d7")] = 0xC0
+    bad_meta[bytes(bad_meta).find(b"Title eight") + 2] = 0xED
+    for raw in docs[:3] + [bad_chunk, bad_id] + docs[3:] + [bad_meta]:
+        pipe.producer.produce("documents_embed", value=bytes(raw))
+    q_ok = [bytearray(pipe.codec.encode("queries_embed", {"query": f"question {i}", "embedding": g.standard_normal(dim).astype(np.float32)}))
+            for i in range(5)]
+    q_bad = bytearray(q_ok[2])
+    q_bad[bytes(q_bad).find(b"question 2")] = 0x80
+    for raw in q_ok[:2] + [q_bad] + q_ok[3:]:
+        pipe.producer.produce("queries_embed", value=bytes(raw))
+    pipe.producer.flush()
+    pipe.run_until_idle()
+    assert len(table) == 6 and sorted(table.document_id) == [f"d{i}" for i in range(6)]
+    assert pipe.stats["quarantined"] == 4 and pipe.stats["searches"] == 4
+    b = Broker(logd)
+    assert b.count("documents_embed.dlq") == 3 and b.count("queries_embed.dlq") == 1 and b.count("search_results") == 4
+    c = Consumer({"log.dir": logd, "group.id": "check"}); c.subscribe(["search_results"])
+    assert [Codec(logd).decode(m.value())["query"] for m in c.consume(10, 0.0)] == ["question 0", "question 1", "question 3", "question 4"]

@@ -244,3 +244,83 @@ def test_native_batch_codecs_roundtrip_and_errors(lib):
     assert lib.sa_wire_decode_queries_embed(data, voff.ctypes.data, vlen.ctypes.data, n, dim, sid + 1, got.ctypes.data,
                                             to2.ctypes.data, tl2.ctypes.data, st.ctypes.data, C.byref(n_ok)) == 0
     assert n_ok.value == 0 and (st == 1).all() and (got == 0).all()
+
+
+def test_native_decoders_survive_mutated_records_and_agree_with_the_generic_codec(lib):
+    """Fuzz of the two batch decoders (1 200 records: random byte flips, truncations, extensions, lengths lying about the
+    payload, non-finite floats, null items), large batches so the threaded path runs: never a crash or a read outside a
+    record; a record the native path accepts (status 0) is exactly what the generic codec decodes; a record the generic
+    codec rejects -- or one holding a non-finite value -- is never accepted."""
+    import ctypes as C
+    from qsa_b200.wire import avro, schemas
+    g = np.random.default_rng(77)
+    dim = 64
+    for topic, sid in (("queries_embed", 100201), ("documents_embed", 100202)):
+        cs = avro.CompiledSchema(schemas.TOPIC_SCHEMAS[topic])
+        header = avro.frame(sid, b"")
+        values = []
+        for i in range(1200):
+            vec = g.standard_normal(dim).astype(np.float32)
+            if topic == "queries_embed":
+                rec = {"query": None if i % 17 == 0 else f"q{i} é", "embedding": vec}
+            else:
+                rec = {"document_id": None if i % 19 == 0 else f"d{i}", "chunk": f"chunk {i}" * (i % 4), "embedding": vec,
+                       "pages": None if i % 2 else str(i), "section_reference": None, "title": f"T{i}" if i % 3 else None,
+                       "fraud_categories": ["a", None, "b"] if i % 5 == 0 else None, "policy_keywords": None,
+                       "char_count": i if i % 7 else None}
+            raw = bytearray(cs.encode(rec, prefix=header))
+            kind = i % 8
+            if kind == 1:                                       # a few flipped bytes anywhere
+                for _ in range(int(g.integers(1, 4))):
+                    raw[int(g.integers(0, len(raw)))] ^= int(g.integers(1, 256))
+            elif kind == 2:
+                raw = raw[:int(g.integers(0, len(raw)))]        # truncated
+            elif kind == 3:
+                raw += bytes(g.integers(0, 256, int(g.integers(1, 9)), dtype=np.uint8))   # trailing bytes
+            elif kind == 4:                                     # a non-finite float somewhere in the array
+                j = int(g.integers(0, dim))
+                k = bytes(raw).find(vec[j].tobytes())
+                if k > 0:
+                    raw[k:k + 4] = np.array([np.inf if i % 16 < 8 else np.nan], np.float32).tobytes()
+            elif kind == 5 and topic == "queries_embed":        # an embedding with a null item (legal Avro, generic path only)
+                v = [float(x) for x in vec]; v[3] = None
+                raw = bytearray(cs.encode({"query": "x", "embedding": v}, prefix=header))
+            values.append(bytes(raw))
+        buf = b"".join(values)
+        vlen = np.array([len(v) for v in values], np.uint32)
+        voff = np.concatenate([[0], np.cumsum(vlen[:-1], dtype=np.uint64)]).astype(np.uint64)
+        n = len(values)
+        vecs = np.full((n, dim), 9.0, np.float32)
+        st = np.empty(n, np.uint8); n_ok = C.c_int()
+        a_off, a_len = np.empty(n, np.uint64), np.empty(n, np.uint32)
+        if topic == "queries_embed":
+            assert lib.sa_wire_decode_queries_embed(buf, voff.ctypes.data, vlen.ctypes.data, n, dim, sid, vecs.ctypes.data,
+                                                    a_off.ctypes.data, a_len.ctypes.data, st.ctypes.data, C.byref(n_ok)) == 0
+        else:
+            b_off, b_len, m_off, m_len = np.empty(n, np.uint64), np.empty(n, np.uint32), np.empty(n, np.uint64), np.empty(n, np.uint32)
+            assert lib.sa_wire_decode_documents_embed(buf, voff.ctypes.data, vlen.ctypes.data, n, dim, sid, vecs.ctypes.data,
+                                                      a_off.ctypes.data, a_len.ctypes.data, b_off.ctypes.data, b_len.ctypes.data,
+                                                      m_off.ctypes.data, m_len.ctypes.data, st.ctypes.data, C.byref(n_ok)) == 0
+        assert n_ok.value == int((st == 0).sum()) and 300 < n_ok.value < n
+        accepted_clean = 0
+        for i, v in enumerate(values):
+            try:
+                rec = cs.decode(v, 5) if (len(v) >= 5 and v[0] == 0 and v[1:5] == header[1:5]) else None
+            except Exception:
+                rec = None
+            emb = None if rec is None else rec.get("embedding")
+            usable = (emb is not None and len(emb) == dim and all(x is not None for x in emb)
+                      and bool(np.isfinite(np.asarray(emb, np.float32)).all()))
+            if st[i] == 0:
+                assert usable, i                                                       # never accepts what it should not
+                assert (vecs[i] == np.asarray(emb, np.float32)).all(), i
+                first = rec["query"] if topic == "queries_embed" else rec["document_id"]
+                got = None if a_len[i] == 0xFFFFFFFF else buf[int(a_off[i]):int(a_off[i]) + int(a_len[i])].decode()
+                assert got == first, i
+                if topic == "documents_embed":
+                    gc = None if b_len[i] == 0xFFFFFFFF else buf[int(b_off[i]):int(b_off[i]) + int(b_len[i])].decode()
+                    assert gc == rec["chunk"], i
+                accepted_clean += i % 8 == 0
+            else:
+                assert (vecs[i] == 0).all(), i                                         # handed over: row zero-filled
+        assert accepted_clean == 150 - (0 if topic == "documents_embed" else len([i for i in range(0, 1200, 8) if i % 17 == 0]))
