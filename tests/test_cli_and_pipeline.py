@@ -643,3 +643,74 @@ def test_strings_that_are_not_utf8_are_quarantined_by_both_codecs(tmp_path, nati
     assert b.count("documents_embed.dlq") == 3 and b.count("queries_embed.dlq") == 1 and b.count("search_results") == 4
     c = Consumer({"log.dir": logd, "group.id": "check"}); c.subscribe(["search_results"])
     assert [Codec(logd).decode(m.value())["query"] for m in c.consume(10, 0.0)] == ["question 0", "question 1", "question 3", "question 4"]
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_streams_native_and_generic_pipelines_agree(tmp_path, seed):
+    """Differential run on random streams: a random mixture of usual, unusual and mutated records (byte flips,
+    truncations, non-UTF-8 strings, null values) on `documents_embed` and `queries_embed`, random batch size -- the native
+    batch path and the generic codec must end with the same table, the same `search_results` bytes in the same order and
+    the same quarantine."""
+    import struct as _s
+    globals()["struct"] = _s
+    dim = 32
+    results = {}
+    for name in ("generic", "native"):
+        g = np.random.default_rng(1000 + seed)
+        logd = str(tmp_path / name)
+        table = VectorTable(PipelinedOracleIndex(dim))
+        pipe = Lab2Pipeline(logd, table, k=3, max_batch=int(g.choice([1, 2, 3, 8, 64])), native=(name == "native"),
+                            score_mode=str(g.choice(["cosine", "atlas"])))
+        vec = lambda: g.standard_normal(dim).astype(np.float32)
+
+        def mutate(raw):
+            raw = bytearray(raw)
+            kind = int(g.integers(0, 6))
+            if kind == 0 and len(raw) > 6:
+                for _ in range(int(g.integers(1, 3))):
+                    raw[int(g.integers(5, len(raw)))] ^= int(g.integers(1, 256))
+            elif kind == 1:
+                raw = raw[:int(g.integers(0, len(raw) + 1))]
+            elif kind == 2:
+                raw += bytes(g.integers(0, 256, int(g.integers(1, 5)), dtype=np.uint8))
+            return bytes(raw)
+        p = Producer({"log.dir": logd})
+        n_docs = int(g.integers(5, 40))
+        for i in range(n_docs):
+            doc_id = None if g.random() < 0.1 else f"d{int(g.integers(0, 25))}"           # repeats = upserts
+            rec = {"document_id": doc_id, "chunk": None if g.random() < 0.1 else f"chunk {i} ü", "embedding": vec()}
+            if g.random() < 0.3:
+                rec.update(title=f"T{i}", pages=str(i), fraud_categories=["x", None], char_count=i)
+            raw = pipe.codec.encode("documents_embed", rec)
+            if g.random() < 0.25:
+                raw = mutate(raw)
+            p.produce("documents_embed", value=raw)
+        odd = _odd_queries_embed_records(pipe.codec, dim, g)
+        n_q = int(g.integers(3, 40))
+        for i in range(n_q):
+            r = g.random()
+            if r < 0.2:
+                raw = odd[int(g.integers(0, len(odd)))]
+            else:
+                raw = pipe.codec.encode("queries_embed", {"query": None if r < 0.3 else f"q{i} é", "embedding": vec()})
+                if r > 0.8:
+                    raw = mutate(raw)
+            p.produce("queries_embed", value=(None if g.random() < 0.03 else raw))
+        p.flush()
+        pipe.run_until_idle()
+
+        def drain(topic):
+            c = Consumer({"log.dir": logd, "group.id": "cmp"}); c.subscribe([topic])
+            return [(m.key(), m.value()) for m in c.consume(1000, 0.0)]
+        results[name] = {
+            "table": (list(table.document_id), list(table.chunk), [dict(m) for m in table.metadata]),
+            "rows": table.index.bits.tobytes(),                      # the vectors as ingested (bf16), tombstones included
+            "search_results": [v for _, v in drain("search_results")],
+            "dlq_q": sorted(drain("queries_embed.dlq"), key=repr), "dlq_d": sorted(drain("documents_embed.dlq"), key=repr),
+            "stats": {k: pipe.stats[k] for k in ("documents", "searches", "quarantined")},
+        }
+    a, b = results["generic"], results["native"]
+    assert a["stats"] == b["stats"], (a["stats"], b["stats"])
+    assert a["table"] == b["table"]
+    assert a["search_results"] == b["search_results"] and a["dlq_q"] == b["dlq_q"] and a["dlq_d"] == b["dlq_d"]
+    assert a["rows"] == b["rows"]
