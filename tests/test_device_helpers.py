@@ -139,3 +139,44 @@ def test_window_bound_never_exceeds_the_global_kl_th_best(lib, seed, kl, tiles):
     allv = np.sort(np.concatenate(lanes))[::-1]
     assert bound <= allv[kl - 1]
     assert (allv >= bound).sum() >= kl
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.integers(0, 2 ** 31), st.sampled_from([16, 32]), st.integers(1, 5))
+def test_list_rule_under_arbitrary_shared_bounds(lib, seed, kl, n_bounds):
+    """Any sequence of shared bounds (tightening or not, arriving at any chunk) leaves the invariants the exactness
+    certificate rests on: (i) every value the list does not hold is <= the dropped bound; (ii) a value that is at or above
+    every bound visible when it arrived, and belongs to the top-KL of all values, is in the list; (iii) the list is sorted
+    (score desc, row asc) and holds no value below the tightest bound visible when that value arrived."""
+    g = np.random.default_rng(seed)
+    n = int(g.integers(1, 400))
+    s = np.round(g.standard_normal(n), 1).astype(np.float32)               # coarse grid: plenty of ties
+    s[g.random(n) < 0.05] = np.nan                                          # masked rows
+    rows = np.arange(n, dtype=np.int32)
+    floor = np.full(n, -np.inf, np.float32)
+    for _ in range(n_bounds):
+        floor[int(g.integers(0, n))] = np.float32(np.round(g.normal(0.5, 0.8), 1))
+    got_s, got_r, drop = run_list(lib, s, rows, kl, floor, want_drop=True)
+    # the bound in force for value i: the max of the bounds that became visible at or before the start of its chunk
+    vis = np.full(n, -np.inf, np.float32)
+    cur = -np.inf
+    for c0 in range(0, n, 32):
+        for i in range(c0, min(n, c0 + 32)):          # a bound attached to value i is applied when value i is staged ...
+            if floor[i] > -np.inf:
+                cur = max(cur, float(floor[i]))
+            vis[i] = cur                               # ... i.e. before the chunk is processed, but in staging order
+    # the hook applies floors while staging the chunk, so within a chunk every bound of that chunk is visible to all of it
+    for c0 in range(0, n, 32):
+        vis[c0:c0 + 32] = vis[min(n, c0 + 32) - 1]
+    held = {int(r) for r in got_r if r >= 0}
+    ok = ~np.isnan(s)
+    rest = [float(s[i]) for i in range(n) if ok[i] and i not in held]
+    assert all(v <= drop for v in rest), (max(rest) if rest else None, drop)                          # (i)
+    order = np.lexsort((rows[ok], -s[ok]))
+    top = set(rows[ok][order[:kl]].tolist())
+    for i in top:
+        if s[i] >= vis[i]:
+            assert i in held, (i, float(s[i]), float(vis[i]))                                      # (ii)
+    hs = [(float(x), int(r)) for x, r in zip(got_s, got_r) if r >= 0]
+    assert hs == sorted(hs, key=lambda t: (-t[0], t[1]))                                             # (iii)
+    assert all(float(s[r]) >= vis[r] for _, r in hs)
