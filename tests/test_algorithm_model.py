@@ -138,3 +138,92 @@ def test_crowds_wherever_they_sit(lib):
     exact3[dup] = 0.4
     got, fixed = search_model(lib, exact3, exact3.astype(np.float32), 2e-4, 18, k)
     assert (got == np.sort(dup)[:k]).all() and fixed == 18      # ties resolve to the lowest rows
+
+
+def window_floors(lib, approx, n_lanes):
+    """Per lane, the floor each of its rows sees under the window bound, for a lock-step interleaving (every lane finishes
+    tile t before anybody starts tile t+1): lane L's bound for its tile t is the (KL/2)-th largest, over the 16 lanes
+    starting at L, of their second-best score after their tile t-1 -- computed by the kernel's own network
+    (sa_debug_window_bound over sa_debug_float_keys keys).  The second bests used are the TRUE ones of each lane's prefix,
+    at least as large as what a lane that already drops rows would publish: a tighter bound than the kernel's, still valid
+    (the rows exist), and so a harder case for the certificate."""
+    n = len(approx)
+    tiles = np.arange(n) // 256
+    lane_rows = [np.flatnonzero(tiles % n_lanes == lane).astype(np.int32) for lane in range(n_lanes)]
+    n_t = max((len(r) + 255) // 256 for r in lane_rows)
+    sb = np.full((n_lanes, n_t), -np.inf, np.float32)          # second best after tile t (lane-local tile index)
+    for lane, rows in enumerate(lane_rows):
+        for t in range(n_t):
+            pre = approx[rows[: (t + 1) * 256]]
+            if len(pre) >= 2:
+                sb[lane, t] = np.partition(pre, -2)[-2]
+    floors = []
+    for lane, rows in enumerate(lane_rows):
+        f = np.full(len(rows), -np.inf, np.float32)
+        for t in range(1, (len(rows) + 255) // 256):
+            win = np.ascontiguousarray(sb[[(lane + i) % n_lanes for i in range(16)], t - 1])
+            key = np.zeros(16, np.uint32); back = np.empty(16, np.float32); below = np.empty(16, np.float32)
+            fin = np.isfinite(win)
+            if fin.any():
+                k2 = np.empty(int(fin.sum()), np.uint32)
+                assert lib.sa_debug_float_keys(ptr(np.ascontiguousarray(win[fin])), int(fin.sum()), ptr(k2), ptr(back), ptr(below)) == 0
+                key[fin] = k2                                   # lanes with fewer than two rows so far: key 0 = unpublished
+            out = np.empty(1, np.uint32)
+            assert lib.sa_debug_window_bound(ptr(key), 1, KL, ptr(out), None) == 0
+            if out[0] != 0:
+                f[t * 256] = win[fin][k2 == out[0]][0]
+        floors.append(f)
+    return lane_rows, floors
+
+
+@pytest.mark.parametrize("n_lanes", [16, 18, 37, 148])
+def test_model_is_exact_with_the_window_bound(lib, n_lanes):
+    """The scan with the window bound in force (every lane's threshold floored by kKL/2 lanes' second bests), then the same
+    merge / certificate / fallback: exact for iid data, for error at the edge of eps, and for crowds of near-ties --
+    scattered (most lanes' second best EQUALS the score to keep) and packed into one tile."""
+    g = np.random.default_rng(100 + n_lanes)
+    eps, k = 2e-4, 10
+    cases = []
+    for trial in range(4):
+        n = int(g.integers(n_lanes * 256 * 2, n_lanes * 256 * 6))
+        exact = g.standard_normal(n) * 0.03
+        cases.append((exact, (exact + g.choice([-eps, eps], n) * (0.999 if trial % 2 else 0.01)).astype(np.float32)))
+    n = n_lanes * 256 * 4
+    exact = g.standard_normal(n) * 0.03
+    exact[g.choice(n, 200, replace=False)] = 0.4               # duplicates everywhere
+    cases.append((exact, exact.astype(np.float32)))
+    exact = g.standard_normal(n) * 0.03
+    exact[5000:5024] = 0.5 + np.arange(24) * 1e-9              # the one-tile crowd, approximate order reversed
+    approx = exact.astype(np.float32)
+    approx[5000:5024] = np.float32(0.5) + (23 - np.arange(24)).astype(np.float32) * np.float32(6e-8)
+    cases.append((exact, approx))
+    tight = 0
+    for ci, (exact, approx) in enumerate(cases):
+        n = len(exact)
+        tiles = np.arange(n) // 256
+        lane_rows, floors = window_floors(lib, approx, n_lanes)
+        lists, drops = [], []
+        for rows, f in zip(lane_rows, floors):
+            s, r, d = lane_list(lib, approx[rows], rows, f)
+            lists.append((s, r)); drops.append(d)
+            tight += int(np.isfinite(f).any())
+        cs = np.concatenate([s for s, _ in lists]); cr = np.concatenate([r for _, r in lists])
+        ok = cr >= 0
+        cs, cr = cs[ok], cr[ok]
+        # the bound is valid: the union still holds the top-KL by approximate score (ties aside, at least their scores)
+        top = np.sort(approx)[::-1][:KL]
+        assert (np.sort(cs)[::-1][:KL] == top).all(), ci
+        order = np.lexsort((cr, -cs))
+        band = np.float32(cs[order[k - 1]]) - np.float32(2 * eps)
+        amb = [d > -np.inf and d >= band for d in drops]
+        sel = cr[cs >= band]
+        if len(sel) > SEL_MAX:
+            amb, sel = [True] * n_lanes, sel[:SEL_MAX]
+        best = set(sel.tolist())
+        for lane in np.flatnonzero(amb):
+            rows = np.flatnonzero(tiles % n_lanes == lane)
+            best.update(rows[exact[rows] >= band].tolist())
+        cand = np.fromiter(best, dtype=np.int64)
+        got = cand[np.lexsort((cand, -exact[cand]))[:k]]
+        assert (got == exact_topk(exact, k)).all(), (ci, n_lanes)
+    assert tight > 0                                            # the window bound really was in force
