@@ -714,3 +714,77 @@ def test_random_streams_native_and_generic_pipelines_agree(tmp_path, seed):
     assert a["table"] == b["table"]
     assert a["search_results"] == b["search_results"] and a["dlq_q"] == b["dlq_q"] and a["dlq_d"] == b["dlq_d"]
     assert a["rows"] == b["rows"]
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_vector_table_against_a_dictionary_model_under_random_operations(tmp_path, seed):
+    """Random upsert batches (repeated ids inside a batch and across batches, null ids, null chunks, metadata), a clear
+    now and then, a checkpoint / restore in the middle: the table must stay equivalent to a plain dictionary -- the live
+    row of an id is its last upsert, every older row of it is tombstoned (all-zero vector), the pre-serialised Avro
+    columns and arenas describe every row, and searching returns what brute force over the live rows returns."""
+    from qsa_b200.operator import _avro_nullable_string
+    g = np.random.default_rng(500 + seed)
+    dim = 16
+    table = VectorTable(OracleIndex(dim))
+    model, anon = {}, []                                   # id -> (chunk, vector, metadata); rows published without an id
+
+    def check(t):
+        n = len(t)
+        assert len(t.chunk) == len(t.metadata) == len(t.avro_document_id) == len(t.avro_chunk) == n == len(t.index)
+        vecs = bf_bits_to_f32(t.index.bits)
+        live = {d: r for r, d in enumerate(t.document_id) if d is not None and t._row_of.get(d) == r}
+        assert set(live) == set(model) and t._row_of == live
+        for d, r in live.items():
+            chunk, vec, meta = model[d]
+            assert t.chunk[r] == chunk and t.metadata[r] == meta and (vecs[r] == bf_round(vec)).all()
+        for r, d in enumerate(t.document_id):
+            if d is not None and live.get(d) != r:
+                assert not vecs[r].any()                   # tombstone
+            assert t.avro_document_id[r] == _avro_nullable_string(d) and t.avro_chunk[r] == _avro_nullable_string(t.chunk[r])
+            for arena, col in ((t.arena_document_id, t.avro_document_id), (t.arena_chunk, t.avro_chunk)):
+                lo, hi = int(arena.off[r]), int(arena.off[r + 1])
+                assert bytes(arena.data[lo:hi]) == col[r]
+        anon_rows = [r for r, d in enumerate(t.document_id) if d is None]
+        assert len(anon_rows) == len(anon)
+        for r, (chunk, vec) in zip(anon_rows, anon):
+            assert t.chunk[r] == chunk and (vecs[r] == bf_round(vec)).all()
+
+    def bf_bits_to_f32(bits):
+        return (bits.astype(np.uint32) << 16).view(np.float32)
+
+    def bf_round(v):
+        from oracle import bruteforce as bf
+        return bf.bf16_bits_to_f32(bf.f32_to_bf16_bits(np.asarray(v, np.float32)))
+
+    for step in range(30):
+        r = g.random()
+        if r < 0.06:
+            table.clear(); model.clear(); anon.clear()
+        elif r < 0.14 and len(table):
+            d = str(tmp_path / f"ckpt{step}")
+            table.save(d, {"documents_embed-0": step})
+            restored = VectorTable(OracleIndex(dim))
+            restored.index.bits = table.index.bits.copy()   # the double has no snapshot(): the vectors travel by hand
+            assert restored.load(d) == len(table) and restored.source_offsets == {"documents_embed-0": step}
+            check(restored)
+            table = restored
+        else:
+            n = int(g.integers(1, 12))
+            ids = [None if g.random() < 0.15 else f"d{int(g.integers(0, 20))}" for _ in range(n)]
+            chunks = [None if g.random() < 0.1 else f"c{step}-{i} é" for i in range(n)]
+            vecs = g.standard_normal((n, dim)).astype(np.float32)
+            metas = [({"title": f"t{step}-{i}"} if g.random() < 0.4 else {}) for i in range(n)]
+            table.upsert_many(ids, chunks, vecs, metas)
+            last = {d: i for i, d in enumerate(ids) if d is not None}
+            for i, d in enumerate(ids):
+                if d is None:
+                    anon.append((chunks[i], vecs[i]))
+                elif last[d] == i:
+                    model[d] = (chunks[i], vecs[i], metas[i])
+        check(table)
+    if len(table):
+        q = g.standard_normal((5, dim)).astype(np.float32)
+        hits = vector_search_agg(table, "embedding", q, 3)
+        for h in hits:
+            for x in h:
+                assert x.document_id is None or table._row_of[x.document_id] == x.row      # never a tombstoned row
