@@ -35,8 +35,8 @@ import time
 import numpy as np
 
 from ..embed.stub import StubEmbedder
-from ..operator import VectorTable, flatten_search_results, rag_prompt, search_results_avro_body, vector_search_agg
-from ..transport.filelog import Consumer, Message, Producer, TopicPartition
+from ..operator import VectorTable, rag_prompt, search_results_avro_body
+from ..transport.filelog import Message
 from ..wire import avro, schemas
 from ..wire.registry import SchemaRegistry
 
